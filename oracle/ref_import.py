@@ -1,0 +1,47 @@
+"""Import the UNMODIFIED reference modules in-process (dev container only; TEST INFRASTRUCTURE).
+
+The reference needs two pip packages that are not installed (``fcn``, ``gdown``); neither is used on
+the hot path (models.py:1-2,206; utils.py:1), so empty stand-ins are put on ``sys.modules`` first.
+Returns ``(models, utils)`` or raises ``FileNotFoundError`` when no reference checkout is present
+(the GPU box has none: nothing that runs there may call this).
+"""
+import importlib
+import os
+import sys
+import types
+
+REF_DIRS = ("/root/reference",)
+
+
+def reference_root():
+    for d in REF_DIRS:
+        if os.path.isfile(os.path.join(d, "models.py")):
+            return d
+    return None
+
+
+def load_reference():
+    root = reference_root()
+    if root is None:
+        raise FileNotFoundError("reference checkout not present")
+    if "fcn" not in sys.modules:
+        fcn = types.ModuleType("fcn")
+        fcn.data = types.SimpleNamespace(cached_download=_no_network)
+        fcn.utils = types.SimpleNamespace()
+        sys.modules["fcn"] = fcn
+    if "gdown" not in sys.modules:
+        sys.modules["gdown"] = types.ModuleType("gdown")
+    if root not in sys.path:
+        sys.path.append(root)
+    # the reference's module names are generic ("models", "utils"): import them under private names
+    mods = []
+    for name in ("models", "utils"):
+        spec = importlib.util.spec_from_file_location("szn_reference_" + name, os.path.join(root, name + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        mods.append(m)
+    return tuple(mods)
+
+
+def _no_network(**kw):
+    raise RuntimeError("no network in this environment")
