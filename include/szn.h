@@ -1,0 +1,118 @@
+/* szn.h — C ABI of libszn.so, the sm_100a implementation of the SZN pixel-embedding hot path.
+ *
+ * The reference (RohanDoshi2018/ZeroshotSemanticSegmentation) has no FFI/plugin boundary: its hot path
+ * is Python calling torch ops.  This header is the boundary a maintainer binds instead (ctypes stub
+ * in INTEGRATION.md); each entry point names the reference lines whose device work it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 or a negative SZN_ERR_* code; szn_last_error() gives the message.
+ *   - the caller owns every buffer (device pointers unless stated), nothing is allocated here,
+ *     nothing synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - dtype: SZN_F32 = fp32 storage, TF32 tensor-core products, fp32 accumulate;
+ *            SZN_BF16 = bf16 storage, bf16 products, fp32 accumulate.
+ *   - trunk activations are NHWC ([B][H][W][C], channels contiguous); weights for the tensor-core
+ *     kernels are [Cout][R*S][Cin] ("OHWI") in the activation dtype; the public tensors of the
+ *     reference API (input image, returned score) stay NCHW fp32.
+ */
+#ifndef SZN_H_
+#define SZN_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SZN_F32 0
+#define SZN_BF16 1
+
+#define SZN_ERR_ARG (-1)
+#define SZN_ERR_CUDA (-2)
+#define SZN_ERR_UNSUPPORTED (-3)
+
+const char* szn_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long szn_launch_count(void);
+int szn_abi_version(void);
+
+/* ---- tensor-core implicit-GEMM convolutions (models.py:45-93 conv1_2..score_fr and their autograd backward) ---- */
+/* y[B,Ho,Wo,*] = act(conv(x[B,H,W,Cin], wt[Cout][R*S][Cin]) + bias) * scale[b][co];  ldo = row stride of y (elements).
+ * 1x1/pad 0 convolutions are run as one flat GEMM over all B*H*W pixels. out_fp32: store raw fp32 regardless of dtype. */
+int szn_conv_fwd(int dtype, const void* x, const void* wt, const float* bias, void* y, int B, int H, int W, int Cin,
+                 int Cout, int R, int S, int pad, int relu, const float* scale, int scale_ld, int out_fp32,
+                 long long ldo, void* stream);
+/* dx[B,H,W,Cin] = conv_transpose(dy[B,Ho,Wo,Cout] (row stride ld_dy), wt) * scale[b][ci] * (relu_ref[B,H,W,Cin] > 0) */
+int szn_conv_dgrad(int dtype, const void* dy, const void* wt, void* dx, int B, int H, int W, int Cin, int Cout, int R,
+                   int S, int pad, const void* relu_ref, const float* scale, int scale_ld, long long ld_dy,
+                   void* stream);
+/* dw[Cout][R*S*Cin] += sum_pixels dy (x) x   (fp32, split-K atomics: zero dw first) */
+int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int R,
+                   int S, int pad, long long ld_dy, void* stream);
+
+/* ---- conv1_1 (models.py:43-44,116): Cin=3, pad=100, CUDA cores; x is the public NCHW fp32 image ---- */
+int szn_conv1_1_fwd(int dtype, const float* x, const float* w_oihw, const float* bias, void* y, int B, int H, int W,
+                    int pad, void* stream);
+/* dw_oihw[64][3][3][3] += ...   (fp32 atomics: zero first) */
+int szn_conv1_1_wgrad(int dtype, const float* x, const void* dy, float* dw_oihw, int B, int H, int W, int pad,
+                      void* stream);
+
+/* ---- MaxPool2d(2, stride=2, ceil_mode=True) (models.py:47,54,63,72,81) on NHWC ---- */
+int szn_pool_fwd(int dtype, const void* in, void* out, int B, int H, int W, int C, void* stream);
+/* dy = route dp to the first maximum of each window; relu_gate additionally zeroes positions where y <= 0 */
+int szn_pool_bwd(int dtype, const void* y, const void* dp, void* dy, int B, int H, int W, int C, int relu_gate,
+                 void* stream);
+
+/* db[C] += column sums of dy[rows][ld]  (bias gradients of every conv; zero db first) */
+int szn_bias_grad(int dtype, const void* dy, float* db, long long rows, int C, long long ld, void* stream);
+
+/* parameter layout conversion between the reference's OIHW fp32 tensors (state_dict layout, models.py:43-98)
+ * and the kernels' [O_pad][R*S][I] layout (rows >= O zero-filled) */
+int szn_pack_weight(int dtype, const float* w_oihw, void* out, int O, int I, int R, int S, int O_pad, void* stream);
+int szn_unpack_wgrad(const float* dw_ohwi, float* g_oihw, int O, int I, int R, int S, void* stream);
+int szn_cast(int dtype, const float* in, void* out, long long n, void* stream);
+
+/* Dropout2d(p=0.5) (models.py:86,91): scale[n] in {0,2}, one value per (image, channel) */
+int szn_dropout_scale(float* scale, int n, unsigned long long seed, void* stream);
+
+/* ---- upscore / seenmask_upscore: ConvTranspose2d(k=64, stride=32) + crop 19 (models.py:94,98,146-151) ----
+ * s: fp32 [B,hs,ws,ld], channels [coff, coff+D).  out / g: NCHW fp32 [B,D,H,W] (the tensors forward() returns). */
+int szn_upsample32_crop_fwd(const float* s, float* out, int B, int D, int H, int W, int hs, int ws, int ld, int coff,
+                            void* stream);
+int szn_upsample32_crop_bwd(int dtype, const float* g, void* ds, int B, int D, int H, int W, int hs, int ws, int ld,
+                            int coff, void* stream);
+/* dense variant for small channel counts (trained 2x2 seenmask head); wd: [Ci][Co][64][64] fp32 */
+int szn_deconv_small_fwd(const float* s, const float* wd, float* out, int B, int Ci, int Co, int H, int W, int hs,
+                         int ws, int ld, int coff, void* stream);
+int szn_deconv_small_dgrad(int dtype, const float* g, const float* wd, void* ds, int B, int Ci, int Co, int H, int W,
+                           int hs, int ws, int ld, int coff, void* stream);
+int szn_deconv_small_wgrad(const float* s, const float* g, float* dwd, int B, int Ci, int Co, int H, int W, int hs,
+                           int ws, int ld, int coff, void* stream);
+
+/* ---- losses (utils.py:19-102).  score NCHW fp32, target int64 [n,h,w] with -1 = ignore.
+ * kind 0 = cosine_loss (utils.py:75-102), 1 = mse_loss (utils.py:50-73).  accum = {sum, n_valid} (fp64, device). */
+int szn_embed_loss_fwd(int kind, const float* score, const long long* target, const float* target_embed,
+                       const float* table, int n, int c, int h, int w, float* stats, double* accum, float* loss,
+                       void* stream);
+int szn_embed_loss_bwd(int kind, const float* score, const long long* target, const float* target_embed,
+                       const float* table, int n, int c, int h, int w, const float* stats, const double* accum,
+                       const float* grad_out, float* dscore, void* stream);
+/* cross_entropy2d (utils.py:19-48) */
+int szn_ce2d_fwd(const float* score, const long long* target, int n, int c, int h, int w, int size_average, float* lse,
+                 double* accum, float* loss, void* stream);
+int szn_ce2d_bwd(const float* score, const long long* target, int n, int c, int h, int w, int size_average,
+                 const float* lse, const double* accum, const float* grad_out, float* dscore, void* stream);
+/* loss from (possibly all-reduced) accumulators: kind 0 (N-sum)/N, 1 sum/N, 2 sum, 3 sum/N */
+int szn_loss_finalize(int kind, const double* accum, float* loss, void* stream);
+
+/* ---- inference (utils.py:159-205) ---- */
+/* infer_lbl: labels = argmax_c <s_p,e_c>/(|s_p| |e_c|), |e_c|==0 -> 1, lowest index on ties */
+int szn_embed_argmax(const float* score, const float* table, int n, int D, int h, int w, int C, float* en_scratch,
+                     long long* labels, void* stream);
+/* stich_seen_unseen_with_mask: mask from seen_mask_score [n,2,h,w] (infer_lbl_szn) or, when that is null,
+ * from target in unseen[] (infer_lbl_forced_unseen) */
+int szn_stitch_labels(const long long* lbl_seen, const long long* lbl_unseen, const float* seen_mask_score,
+                      const long long* target, const long long* unseen, int n_unseen, int n, int h, int w,
+                      long long* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SZN_H_ */

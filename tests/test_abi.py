@@ -1,0 +1,62 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol include/szn.h declares;
+the module surface matches the reference's (no compute calls: there is no GPU here)."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "szn.h")).read()
+    return sorted(set(re.findall(r"\b(szn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from zeroshotsemanticsegmentation_b200 import _lib
+    lib = _lib.load()
+    names = header_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libszn.so does not export %s" % n
+    # every bound signature is declared in the header and vice versa
+    assert set(_lib.SIGNATURES) | {"szn_last_error", "szn_launch_count", "szn_abi_version"} == set(names)
+
+
+def test_no_cpu_fallback():
+    import zeroshotsemanticsegmentation_b200 as szn
+    m = szn.FCN32s(4)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(torch.zeros(1, 3, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        szn.utils.cosine_loss(torch.zeros(1, 4, 2, 2), torch.zeros(1, 2, 2, dtype=torch.long),
+                              torch.zeros(1, 4, 2, 2))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "zeroshotsemanticsegmentation_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("no oracle", "")
+
+
+def test_module_surface_matches_reference():
+    import torch.nn as nn
+    import zeroshotsemanticsegmentation_b200 as szn
+    from oracle import szn_oracle as O
+    m = szn.FCN32s(20)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in O.init_params(20).items()}
+    assert torch.equal(m.upscore.weight.detach(), O.upsampling_weight(20, 20))
+    vgg = nn.Module()
+    feats = []
+    for row in O.TRUNK:
+        feats.append(nn.MaxPool2d(2) if len(row) == 1 else nn.Conv2d(row[1], row[2], 3, padding=1))
+    vgg.features = nn.Sequential(*feats)
+    vgg.classifier = nn.Sequential(nn.Linear(25088, 4096), nn.ReLU(), nn.Dropout(), nn.Linear(4096, 4096))
+    m.copy_params_from_vgg16(vgg)
+    assert torch.equal(m.conv3_2.weight, vgg.features[7].weight)
+    assert torch.equal(m.fc6.weight.view(4096, -1), vgg.classifier[0].weight)

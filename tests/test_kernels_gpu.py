@@ -1,0 +1,287 @@
+"""Per-kernel parity tests (GPU): every C-ABI op of libszn.so against the CPU fp32 oracle ops.
+
+Inputs are pre-rounded to the kernel's storage type (TF32 / bf16), so the tensor-core products are exact
+and the only difference to the fp32 CPU result is accumulation order: tolerances are tight (1e-4 .. 1e-3)
+and any layout / descriptor / indexing bug shows up as O(1) error.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import szn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def lib():
+    from zeroshotsemanticsegmentation_b200 import _lib
+    return _lib
+
+
+def round_to(t, prec):
+    if prec == "bf16":
+        return t.bfloat16().float()
+    i = t.contiguous().view(torch.int32)
+    i = ((i + 0xFFF + ((i >> 13) & 1)) >> 13) << 13
+    return i.view(torch.float32)
+
+
+def tdtype(prec):
+    return torch.bfloat16 if prec == "bf16" else torch.float32
+
+
+def dcode(prec):
+    return 1 if prec == "bf16" else 0
+
+
+def nhwc(t, prec):  # NCHW fp32 cpu -> NHWC device tensor of the storage type
+    return t.permute(0, 2, 3, 1).contiguous().to(DEV).to(tdtype(prec))
+
+
+def from_nhwc(t):
+    return t.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def ohwi(w, prec, o_pad=None):
+    O_, I, R, S = w.shape
+    out = w.permute(0, 2, 3, 1).reshape(O_, R * S, I)
+    if o_pad and o_pad > O_:
+        out = torch.cat([out, torch.zeros(o_pad - O_, R * S, I)], 0)
+    return out.contiguous().to(DEV).to(tdtype(prec))
+
+
+def relerr(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k, pad
+    (2, 20, 37, 64, 64, 3, 1),
+    (1, 9, 9, 128, 256, 3, 1),
+    (1, 45, 45, 64, 128, 3, 1),
+    (2, 9, 10, 64, 128, 7, 0),
+    (2, 5, 7, 256, 320, 1, 0),
+    (1, 23, 23, 128, 512, 3, 1),
+]
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd(prec, case):
+    B, H, W, Cin, Cout, k, pad = case
+    g = torch.Generator().manual_seed(1)
+    x = round_to(torch.randn(B, Cin, H, W, generator=g), prec)
+    w = round_to(torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5, prec)
+    b = torch.randn(Cout, generator=g)
+    scale = (torch.rand(B, Cout, generator=g) < 0.5).float() * 2
+    ref = F.relu(F.conv2d(x, w, b, padding=pad)) * scale[:, :, None, None]
+    Ho, Wo = ref.shape[2:]
+    y = torch.full((B, Ho, Wo, Cout), float("nan"), device=DEV, dtype=tdtype(prec))
+    L = lib()
+    L.call("szn_conv_fwd", dcode(prec), nhwc(x, prec).data_ptr(), ohwi(w, prec).data_ptr(), b.to(DEV).data_ptr(),
+           y.data_ptr(), B, H, W, Cin, Cout, k, k, pad, 1, scale.to(DEV).data_ptr(), Cout, 0, Cout, st())
+    torch.cuda.synchronize()
+    got = from_nhwc(y)
+    tol = 1e-3 if prec == "tf32" else 1e-2  # the kernel rounds its output to the storage type
+    e = relerr(got, ref)
+    print("conv_fwd", prec, case, "relerr", e)
+    assert e < tol
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_conv_fwd_fp32_out_no_relu(prec):
+    B, H, W, Cin, Cout = 2, 5, 7, 128, 64
+    g = torch.Generator().manual_seed(2)
+    x = round_to(torch.randn(B, Cin, H, W, generator=g), prec)
+    w = round_to(torch.randn(Cout - 10, Cin, 1, 1, generator=g) / Cin ** 0.5, prec)
+    b = torch.cat([torch.randn(Cout - 10, generator=g), torch.zeros(10)])
+    ref = F.conv2d(x, w, b[:Cout - 10])
+    y = torch.full((B, H, W, Cout), float("nan"), device=DEV, dtype=torch.float32)
+    L = lib()
+    L.call("szn_conv_fwd", dcode(prec), nhwc(x, prec).data_ptr(), ohwi(w, prec, Cout).data_ptr(), b.to(DEV).data_ptr(),
+           y.data_ptr(), B, H, W, Cin, Cout, 1, 1, 0, 0, None, 0, 1, Cout, st())
+    torch.cuda.synchronize()
+    got = from_nhwc(y)
+    assert relerr(got[:, :Cout - 10], ref) < 1e-5
+    assert (got[:, Cout - 10:] == 0).all()
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_dgrad(prec, case):
+    B, H, W, Cin, Cout, k, pad = case
+    if Cin % 64 and prec == "bf16":
+        pytest.skip("Cin granularity")
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, Cin, H, W, generator=g).requires_grad_(True)
+    w = round_to(torch.randn(Cout, Cin, k, k, generator=g) / (Cout * k * k) ** 0.5, prec)
+    y = F.conv2d(x, w, padding=pad)
+    dy = round_to(torch.randn(y.shape, generator=g), prec)
+    ref_act = torch.randn(B, Cin, H, W, generator=g)  # the layer input whose sign gates the gradient
+    scale = (torch.rand(B, Cin, generator=g) < 0.5).float() * 2
+    (dx,) = torch.autograd.grad(y, x, dy)
+    ref = dx * scale[:, :, None, None] * (ref_act > 0)
+    out = torch.full((B, H, W, Cin), float("nan"), device=DEV, dtype=tdtype(prec))
+    L = lib()
+    L.call("szn_conv_dgrad", dcode(prec), nhwc(dy, prec).data_ptr(), ohwi(w, prec).data_ptr(), out.data_ptr(), B, H, W,
+           Cin, Cout, k, k, pad, nhwc(ref_act, prec).data_ptr(), scale.to(DEV).data_ptr(), Cin, Cout, st())
+    torch.cuda.synchronize()
+    got = from_nhwc(out)
+    e = relerr(got, ref)
+    print("conv_dgrad", prec, case, "relerr", e)
+    assert e < (1e-3 if prec == "tf32" else 1e-2)
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_wgrad(prec, case):
+    B, H, W, Cin, Cout, k, pad = case
+    g = torch.Generator().manual_seed(4)
+    x = round_to(torch.randn(B, Cin, H, W, generator=g), prec)
+    w = torch.zeros(Cout, Cin, k, k, requires_grad=True)
+    y = F.conv2d(x, w, padding=pad)
+    dy = round_to(torch.randn(y.shape, generator=g), prec)
+    (dw,) = torch.autograd.grad(y, w, dy)
+    ref = dw.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin)
+    out = torch.zeros((Cout, k * k * Cin), device=DEV, dtype=torch.float32)
+    L = lib()
+    L.call("szn_conv_wgrad", dcode(prec), nhwc(x, prec).data_ptr(), nhwc(dy, prec).data_ptr(), out.data_ptr(), B, H, W,
+           Cin, Cout, k, k, pad, Cout, st())
+    torch.cuda.synchronize()
+    e = relerr(out.cpu(), ref)
+    print("conv_wgrad", prec, case, "relerr", e)
+    assert e < 1e-4
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_conv1_1(prec):
+    B, H, W = 2, 13, 21
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 3, H, W, generator=g) * 50
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.1).requires_grad_(True)
+    b = torch.randn(64, generator=g)
+    y = F.relu(F.conv2d(x, w, b, padding=100))
+    Ho, Wo = y.shape[2:]
+    out = torch.empty((B, Ho, Wo, 64), device=DEV, dtype=tdtype(prec))
+    L = lib()
+    L.call("szn_conv1_1_fwd", dcode(prec), x.to(DEV).data_ptr(), w.detach().to(DEV).data_ptr(), b.to(DEV).data_ptr(),
+           out.data_ptr(), B, H, W, 100, st())
+    torch.cuda.synchronize()
+    assert relerr(from_nhwc(out), y.detach()) < (1e-3 if prec == "tf32" else 1e-2)
+    dy = round_to(torch.randn(y.shape, generator=g), prec)
+    pre = F.conv2d(x, w, padding=100)
+    (dw,) = torch.autograd.grad(pre, w, dy)
+    gw = torch.zeros((64, 3, 3, 3), device=DEV)
+    L.call("szn_conv1_1_wgrad", dcode(prec), x.to(DEV).data_ptr(), nhwc(dy, prec).data_ptr(), gw.data_ptr(), B, H, W, 100,
+           st())
+    torch.cuda.synchronize()
+    assert relerr(gw.cpu(), dw) < 1e-4
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("hw", [(7, 9), (8, 8), (45, 23)])
+def test_pool(prec, hw):
+    B, C = 2, 64
+    H, W = hw
+    g = torch.Generator().manual_seed(6)
+    # ReLU output with many exact zeros and exact ties inside windows
+    y = round_to(F.relu(torch.randn(B, C, H, W, generator=g)), prec)
+    y[:, :, 0:2, 0:2] = y[:, :, 0:1, 0:1]  # exact non-zero ties: the first position must win
+    y.requires_grad_(True)
+    p = F.max_pool2d(y, 2, stride=2, ceil_mode=True)
+    out = torch.empty((B, p.shape[2], p.shape[3], C), device=DEV, dtype=tdtype(prec))
+    L = lib()
+    yd = nhwc(y.detach(), prec)
+    L.call("szn_pool_fwd", dcode(prec), yd.data_ptr(), out.data_ptr(), B, H, W, C, st())
+    torch.cuda.synchronize()
+    assert torch.equal(from_nhwc(out), p.detach())
+    dp = round_to(torch.randn(p.shape, generator=g), prec)
+    (dy,) = torch.autograd.grad(p, y, dp)
+    ref = dy * (y.detach() > 0)
+    dyo = torch.empty((B, H, W, C), device=DEV, dtype=tdtype(prec))
+    L.call("szn_pool_bwd", dcode(prec), yd.data_ptr(), nhwc(dp, prec).data_ptr(), dyo.data_ptr(), B, H, W, C, 1, st())
+    torch.cuda.synchronize()
+    assert torch.equal(from_nhwc(dyo), ref)
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_bias_grad_pack_unpack(prec):
+    g = torch.Generator().manual_seed(7)
+    rows, C, ld = 1000, 320, 320
+    dy = round_to(torch.randn(rows, ld, generator=g), prec)
+    db = torch.zeros(C, device=DEV)
+    L = lib()
+    L.call("szn_bias_grad", dcode(prec), dy.to(DEV).to(tdtype(prec)).data_ptr(), db.data_ptr(), rows, C, ld, st())
+    torch.cuda.synchronize()
+    assert relerr(db.cpu(), dy.sum(0)) < 1e-5
+    w = torch.randn(5, 64, 3, 3, generator=g)
+    out = torch.empty((8, 9, 64), device=DEV, dtype=tdtype(prec))
+    L.call("szn_pack_weight", dcode(prec), w.to(DEV).data_ptr(), out.data_ptr(), 5, 64, 3, 3, 8, st())
+    torch.cuda.synchronize()
+    ref = round_to(w, prec).permute(0, 2, 3, 1).reshape(5, 9, 64)
+    assert torch.equal(out.float().cpu()[:5], ref) and (out.float().cpu()[5:] == 0).all()
+    dw = torch.randn(5, 9, 64, generator=g)
+    gg = torch.empty((5, 64, 3, 3), device=DEV)
+    L.call("szn_unpack_wgrad", dw.to(DEV).data_ptr(), gg.data_ptr(), 5, 64, 3, 3, st())
+    torch.cuda.synchronize()
+    assert torch.equal(gg.cpu(), dw.reshape(5, 3, 3, 64).permute(0, 3, 1, 2))
+
+
+@pytest.mark.parametrize("HW", [(37, 53), (64, 96)])
+def test_upsample_and_small_deconv(HW):
+    H, W = HW
+    B, D = 2, 20
+    hs, ws = (H + 198 + 31) // 32 - 6, (W + 198 + 31) // 32 - 6
+    # trunk geometry: 5 ceil-mode pools then 7x7 valid
+    def geom(n):
+        n = n + 198
+        for _ in range(5):
+            n = (n + 1) // 2
+        return n - 6
+    hs, ws = geom(H), geom(W)
+    ld = 32
+    g = torch.Generator().manual_seed(8)
+    s = torch.randn(B, hs, ws, ld, generator=g)
+    s_nchw = s.permute(0, 3, 1, 2).contiguous()
+    wdiag = O.upsampling_weight(D, D)
+    sref = s_nchw[:, :D].clone().requires_grad_(True)
+    full = F.conv_transpose2d(sref, wdiag, stride=32)[:, :, 19:19 + H, 19:19 + W]
+    L = lib()
+    out = torch.empty((B, D, H, W), device=DEV)
+    L.call("szn_upsample32_crop_fwd", s.to(DEV).data_ptr(), out.data_ptr(), B, D, H, W, hs, ws, ld, 0, st())
+    torch.cuda.synchronize()
+    assert relerr(out.cpu(), full.detach()) < 1e-5
+    gout = torch.randn(B, D, H, W, generator=g)
+    (ds_ref,) = torch.autograd.grad(full, sref, gout)
+    ds = torch.zeros((B, hs, ws, ld), device=DEV)
+    L.call("szn_upsample32_crop_bwd", 0, gout.to(DEV).data_ptr(), ds.data_ptr(), B, D, H, W, hs, ws, ld, 0, st())
+    torch.cuda.synchronize()
+    got = ds.cpu().permute(0, 3, 1, 2)[:, :D]
+    assert relerr(got, round_to(ds_ref, "tf32")) < 1e-3
+    # dense 2x2 head at channel offset D
+    wd = torch.randn(2, 2, 64, 64, generator=g).requires_grad_(True)
+    s2 = s_nchw[:, D:D + 2].clone().requires_grad_(True)
+    y2 = F.conv_transpose2d(s2, wd, stride=32)[:, :, 19:19 + H, 19:19 + W]
+    o2 = torch.empty((B, 2, H, W), device=DEV)
+    L.call("szn_deconv_small_fwd", s.to(DEV).data_ptr(), wd.detach().to(DEV).data_ptr(), o2.data_ptr(), B, 2, 2, H, W,
+           hs, ws, ld, D, st())
+    torch.cuda.synchronize()
+    assert relerr(o2.cpu(), y2.detach()) < 1e-5
+    g2 = torch.randn(B, 2, H, W, generator=g)
+    ds2_ref, dwd_ref = torch.autograd.grad(y2, (s2, wd), g2)
+    ds2 = torch.zeros((B, hs, ws, ld), device=DEV)
+    L.call("szn_deconv_small_dgrad", 0, g2.to(DEV).data_ptr(), wd.detach().to(DEV).data_ptr(), ds2.data_ptr(), B, 2, 2, H,
+           W, hs, ws, ld, D, st())
+    dwd = torch.empty((2, 2, 64, 64), device=DEV)
+    L.call("szn_deconv_small_wgrad", s.to(DEV).data_ptr(), g2.to(DEV).data_ptr(), dwd.data_ptr(), B, 2, 2, H, W, hs, ws,
+           ld, D, st())
+    torch.cuda.synchronize()
+    assert relerr(ds2.cpu().permute(0, 3, 1, 2)[:, D:D + 2], round_to(ds2_ref, "tf32")) < 1e-3
+    assert relerr(dwd.cpu(), dwd_ref) < 1e-4

@@ -1,0 +1,162 @@
+"""End-to-end parity (GPU): FCN32s forward / backward through the drop-in module against the golden
+vectors of the unmodified reference and against the CPU oracle (tf32 path: <= 1e-3 relative forward)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import szn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def build(n_class, seed, precision="tf32"):
+    import zeroshotsemanticsegmentation_b200 as szn
+    m = szn.FCN32s(n_class, precision=precision)
+    m.load_state_dict(O.init_params(n_class, seed))
+    return m.to(DEV)
+
+
+def test_forward_backward_ce21_golden(golden):
+    """BASELINE configs[0] family (n_class=21, cross_entropy2d sum), small odd size 37x53."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    g = golden("ce21_37x53")
+    m = build(21, int(g["seed"])).eval()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    t = torch.from_numpy(g["target"]).long().to(DEV)
+    score = m(x, mode="fcn")
+    assert score.shape == (1, 21, 37, 53) and score.is_contiguous() and score.dtype == torch.float32
+    e = rel(score.detach().cpu().numpy(), g["score"])
+    print("forward rel err (tf32)", e)
+    assert e < 1e-3
+    loss = U.cross_entropy2d(score, t)
+    assert abs(loss.item() - float(g["loss"])) < 1e-3 * float(g["loss"])
+    loss.backward()
+    for name, tol in (("score_fr.weight", 1e-2), ("score_fr.bias", 1e-2), ("conv1_1.weight", 1e-2),
+                      ("conv1_1.bias", 1e-2), ("fc7.bias", 1e-2)):
+        got = dict(m.named_parameters())[name].grad.cpu().numpy()
+        e = rel(got, g[name.replace(".", "__") + "__grad"])
+        print(name, "grad rel err", e)
+        assert e < tol
+    assert rel(m.conv3_2.weight.grad[::16, ::16].cpu().numpy(), g["conv3_2__weight__grad_sub"]) < 1e-2
+    assert rel(m.fc6.weight.grad[::256, ::64].cpu().numpy(), g["fc6__weight__grad_sub"]) < 1e-2
+    agree = (score.detach().max(1)[1].cpu().numpy() == g["lbl"]).mean()
+    print("argmax agreement", agree)
+    assert agree > 0.995
+
+
+def test_forward_256_golden(golden):
+    """BASELINE configs[0]: 1x3x256x256, 21 classes, forward + CE loss."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    g = golden("ce21_256x256")
+    m = build(21, int(g["seed"])).eval()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    t = torch.from_numpy(g["target"]).long().to(DEV)
+    with torch.no_grad():
+        score = m(x)
+    assert rel(score[:, :, ::8, ::8].cpu().numpy(), g["score_sub"]) < 1e-3
+    loss = U.cross_entropy2d(score, t)
+    assert abs(loss.item() - float(g["loss"])) < 1e-3 * float(g["loss"])
+
+
+def test_embedding_heads_cos_golden(golden):
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    g = golden("cos_voc20_2x64x96")
+    tab = torch.from_numpy(g["table"]).float()
+    m = build(tab.shape[1], int(g["seed"])).eval()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    t = torch.from_numpy(g["target"]).long().to(DEV)
+    f, s = m(x, mode="both")
+    assert rel(f.detach().cpu().numpy(), g["score"]) < 1e-3
+    assert rel(s.detach().cpu().numpy(), g["seenmask_score"]) < 1e-3
+    loss = U.cosine_loss(f, t, table=tab.to(DEV))
+    want = (g["loss_per_sample"] * g["nvalid"]).sum() / g["nvalid"].sum()
+    assert abs(loss.item() - want) < 1e-4
+    loss.backward()
+    assert rel(m.score_fr.weight.grad.cpu().numpy(), g["score_fr__weight__grad"]) < 1e-2
+    assert rel(m.conv1_1.weight.grad.cpu().numpy(), g["conv1_1__weight__grad"]) < 2e-2
+    assert rel(m.conv5_3.weight.grad[::32, ::32].cpu().numpy(), g["conv5_3__weight__grad_sub"]) < 1e-2
+    lbl = U.infer_lbl(f.detach(), tab.to(DEV))
+    print("label agreement vs reference", (lbl == g["lbl"]).mean())
+    assert (lbl == g["lbl"]).mean() > 0.99
+
+
+def test_mode_errors_and_seenmask_phase(golden):
+    """trainer_seenmask.py:50-81: only the seenmask head is trainable; CE mean over the binary target."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    g = golden("cos_voc20_2x64x96")
+    tab = torch.from_numpy(g["table"]).float()
+    m = build(tab.shape[1], int(g["seed"])).eval()
+    with pytest.raises(Exception, match="unexpected forward mode"):
+        m(torch.zeros(1, 3, 32, 32, device=DEV), mode="nope")
+    for p in m.parameters():
+        p.requires_grad = False
+    for p in list(m.seenmask_score.parameters()) + list(m.seenmask_upscore.parameters()):
+        p.requires_grad = True
+    x = torch.from_numpy(g["x"][:1]).to(DEV)
+    t = torch.from_numpy(g["target"][:1]).long()
+    smt = O.seenmask_target(t, list(g["train_unseen"]), tab.shape[0]).to(DEV)
+    s = m(x, mode="seenmask")
+    loss = U.cross_entropy2d(s, smt, size_average=True)
+    assert abs(loss.item() - g["seenmask_loss"][0]) < 1e-3
+    loss.backward()
+    assert m.conv1_1.weight.grad is None and m.score_fr.weight.grad is None
+    # oracle gradient of the head
+    p = {k: v.clone().requires_grad_(k.startswith("seenmask")) for k, v in O.init_params(tab.shape[1], int(g["seed"])).items()}
+    so = O.forward(torch.from_numpy(g["x"][:1]), p, "seenmask")
+    O.cross_entropy2d(so, smt.cpu(), size_average=True).backward()
+    assert rel(m.seenmask_score.weight.grad.cpu().numpy(), p["seenmask_score.weight"].grad.numpy()) < 1e-2
+    assert rel(m.seenmask_upscore.weight.grad.cpu().numpy(), p["seenmask_upscore.weight"].grad.numpy()) < 1e-2
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_train_mode_dropout_masks_and_bf16(precision):
+    """train(): Dropout2d masks injected so the oracle can replay them; bf16 path within its own tolerance."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    D, C, H, W, B = 20, 21, 48, 40, 2
+    params = O.init_params(D, seed=21)
+    x, lab, table = O.synth_batch(B, H, W, C, D, seed=21, block=8)
+    g = torch.Generator().manual_seed(5)
+    masks = ((torch.rand(B, 4096, generator=g) < 0.5).float(), (torch.rand(B, 4096, generator=g) < 0.5).float())
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    f_ref = O.forward(x, pr, "fcn", drop_masks=masks)
+    loss_ref = O.mse_loss(f_ref, lab, O.target_embed_from_labels(lab, table))
+    loss_ref.backward()
+    import zeroshotsemanticsegmentation_b200 as szn
+    m = szn.FCN32s(D, precision=precision)
+    m.load_state_dict(params)
+    m = m.to(DEV).train()
+    m._forced_drop_masks = masks
+    f = m(x.to(DEV))
+    loss = U.mse_loss(f, lab.to(DEV), table=table.to(DEV))
+    loss.backward()
+    tol_f, tol_g = (1e-3, 1e-2) if precision == "tf32" else (2e-2, 8e-2)
+    e = rel(f.detach().cpu().numpy(), f_ref.detach().numpy())
+    print(precision, "forward rel err", e)
+    assert e < tol_f
+    for name in ("fc6.weight", "fc7.weight", "conv4_2.weight", "conv2_1.bias", "conv1_2.weight"):
+        ge = rel(dict(m.named_parameters())[name].grad.cpu().numpy(), pr[name].grad.numpy())
+        print(precision, name, "grad rel err", ge)
+        assert ge < tol_g
+    # random masks: about half of the channels dropped, scaled by 2
+    m._forced_drop_masks = None
+    f2 = m(x.to(DEV))
+    assert torch.isfinite(f2).all()
+
+
+def test_state_dict_and_get_parameters_contract():
+    """train.py:302-331 walks named_modules(); state_dict keys/shapes must equal the reference's."""
+    import torch.nn as nn
+    import zeroshotsemanticsegmentation_b200 as szn
+    m = szn.FCN32s(20)
+    ref_shapes = {k: tuple(v.shape) for k, v in O.init_params(20).items()}
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == ref_shapes
+    allowed = (nn.Conv2d, nn.ConvTranspose2d, nn.ReLU, nn.MaxPool2d, nn.Dropout2d, nn.Sequential, szn.FCN32s)
+    for _, mod in m.named_modules():
+        assert isinstance(mod, allowed)
+    assert m.upscore.bias is None and m.seenmask_upscore.bias is None

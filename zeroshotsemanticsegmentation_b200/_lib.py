@@ -1,0 +1,87 @@
+"""ctypes binding of ``libszn.so`` (C ABI declared in ``include/szn.h``).
+
+There is no CPU fallback: if the shared library is missing or a call fails, a ``RuntimeError`` is
+raised.  Build with ``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C
+zeroshotsemanticsegmentation_b200/csrc``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libszn.so")
+
+I, LL, P, ULL = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_ulonglong
+
+# name -> argtypes (must mirror include/szn.h; tests/test_abi.py checks every symbol is exported)
+SIGNATURES = {
+    "szn_conv_fwd": [I, P, P, P, P, I, I, I, I, I, I, I, I, I, P, I, I, LL, P],
+    "szn_conv_dgrad": [I, P, P, P, I, I, I, I, I, I, I, I, P, P, I, LL, P],
+    "szn_conv_wgrad": [I, P, P, P, I, I, I, I, I, I, I, I, LL, P],
+    "szn_conv1_1_fwd": [I, P, P, P, P, I, I, I, I, P],
+    "szn_conv1_1_wgrad": [I, P, P, P, I, I, I, I, P],
+    "szn_pool_fwd": [I, P, P, I, I, I, I, P],
+    "szn_pool_bwd": [I, P, P, P, I, I, I, I, I, P],
+    "szn_bias_grad": [I, P, P, LL, I, LL, P],
+    "szn_pack_weight": [I, P, P, I, I, I, I, I, P],
+    "szn_unpack_wgrad": [P, P, I, I, I, I, P],
+    "szn_cast": [I, P, P, LL, P],
+    "szn_dropout_scale": [P, I, ULL, P],
+    "szn_upsample32_crop_fwd": [P, P, I, I, I, I, I, I, I, I, P],
+    "szn_upsample32_crop_bwd": [I, P, P, I, I, I, I, I, I, I, I, P],
+    "szn_deconv_small_fwd": [P, P, P, I, I, I, I, I, I, I, I, I, P],
+    "szn_deconv_small_dgrad": [I, P, P, P, I, I, I, I, I, I, I, I, I, P],
+    "szn_deconv_small_wgrad": [P, P, P, I, I, I, I, I, I, I, I, I, P],
+    "szn_embed_loss_fwd": [I, P, P, P, P, I, I, I, I, P, P, P, P],
+    "szn_embed_loss_bwd": [I, P, P, P, P, I, I, I, I, P, P, P, P, P],
+    "szn_ce2d_fwd": [P, P, I, I, I, I, I, P, P, P, P],
+    "szn_ce2d_bwd": [P, P, I, I, I, I, I, P, P, P, P, P],
+    "szn_loss_finalize": [I, P, P, P],
+    "szn_embed_argmax": [P, P, I, I, I, I, I, P, P, P],
+    "szn_stitch_labels": [P, P, P, P, P, I, I, I, I, P, P],
+}
+
+F32, BF16 = 0, 1
+
+_lib = None
+
+
+def load():
+    """Load libszn.so once; raises RuntimeError (never falls back) when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            "libszn.so is not built (%s): run `make -C zeroshotsemanticsegmentation_b200/csrc` "
+            "or __graft_entry__.build(); there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = I
+    lib.szn_last_error.restype = ctypes.c_char_p
+    lib.szn_launch_count.restype = LL
+    lib.szn_abi_version.restype = I
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.szn_last_error().decode()))
+
+
+def launch_count():
+    return int(load().szn_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,401 @@
+// CUDA-core kernels of the trunk that are HBM-bound or too thin for tensor tiles:
+// conv1_1 (Cin=3, pad=100; models.py:43), 2x2 ceil-mode max-pool fwd/bwd (models.py:47..81),
+// bias gradients, weight layout packing, Dropout2d channel masks (models.py:86,91).
+#include "szn_internal.h"
+#include "szn_ptx.cuh"
+
+namespace szn {
+
+static char g_err[512] = "";
+static long long g_launches = 0;
+int set_error(int code, const char* msg) {
+  snprintf(g_err, sizeof g_err, "%s", msg);
+  return code;
+}
+void count_launch() { ++g_launches; }
+
+template <typename T>
+__device__ __forceinline__ T from_float(float f);
+template <>
+__device__ __forceinline__ float from_float<float>(float f) { return to_tf32(f); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float f) { return __float2bfloat16_rn(f); }
+template <typename T>
+__device__ __forceinline__ float as_float(T v);
+template <>
+__device__ __forceinline__ float as_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float as_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ------------------------------------------------------------------------------------------------
+// conv1_1 forward: x NCHW fp32 [B,3,H,W] -> y NHWC [B,Ho,Wo,64], Ho = H + 2*pad - 2, bias + ReLU.
+// One thread = one output pixel x 64 channels; the CTA's 128 pixels are contiguous in NHWC, so the
+// tile is staged in shared memory and written back with coalesced 16-byte stores.
+// Pixels whose 3x3 window lies entirely in the padding (47% of them at 512x512) are relu(bias).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) conv1_1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*OIHW [64][3][3][3]*/,
+                                                          const float* __restrict__ bias, T* __restrict__ y, int B, int H,
+                                                          int W, int Ho, int Wo, int pad) {
+  __shared__ __align__(16) float sw[27 * 64];  // [k][co]
+  __shared__ float sb[64];
+  __shared__ __align__(16) T tile[128 * 64];
+  for (int i = threadIdx.x; i < 27 * 64; i += 128) {
+    const int co = i & 63, k = i >> 6;
+    const int tap = k / 3, c = k - tap * 3;
+    sw[k * 64 + co] = w[co * 27 + c * 9 + tap];  // OIHW -> [tap][ci] order
+  }
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long total = (long long)B * Ho * Wo;
+  const long long p0 = (long long)blockIdx.x * 128;
+  const long long pix = p0 + threadIdx.x;
+  if (pix < total) {
+    const int xo = (int)(pix % Wo);
+    const int yo = (int)((pix / Wo) % Ho);
+    const int b = (int)(pix / ((long long)Wo * Ho));
+    float in[27];
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int yi = yo + r - pad, xi = xo + s - pad;
+        const bool ok = yi >= 0 && yi < H && xi >= 0 && xi < W;
+        any |= ok;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          in[(r * 3 + s) * 3 + c] = ok ? __ldg(x + (((long long)b * 3 + c) * H + yi) * W + xi) : 0.f;
+      }
+    T* trow = tile + threadIdx.x * 64;
+    if (!any) {
+#pragma unroll 8
+      for (int co = 0; co < 64; ++co) trow[co] = from_float<T>(fmaxf(sb[co], 0.f));
+    } else {
+#pragma unroll 2
+      for (int c4 = 0; c4 < 64; c4 += 4) {
+        float a0 = sb[c4], a1 = sb[c4 + 1], a2 = sb[c4 + 2], a3 = sb[c4 + 3];
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+          const float4 wv = *reinterpret_cast<const float4*>(sw + k * 64 + c4);
+          a0 = fmaf(in[k], wv.x, a0);
+          a1 = fmaf(in[k], wv.y, a1);
+          a2 = fmaf(in[k], wv.z, a2);
+          a3 = fmaf(in[k], wv.w, a3);
+        }
+        trow[c4] = from_float<T>(fmaxf(a0, 0.f));
+        trow[c4 + 1] = from_float<T>(fmaxf(a1, 0.f));
+        trow[c4 + 2] = from_float<T>(fmaxf(a2, 0.f));
+        trow[c4 + 3] = from_float<T>(fmaxf(a3, 0.f));
+      }
+    }
+  }
+  __syncthreads();
+  long long npix = total - p0;
+  if (npix > 128) npix = 128;
+  const int n16 = (int)(npix * 64 * sizeof(T) / 16);
+  uint4* dst = reinterpret_cast<uint4*>(y + p0 * 64);
+  const uint4* src = reinterpret_cast<const uint4*>(tile);
+  for (int i = threadIdx.x; i < n16; i += 128) dst[i] = src[i];
+}
+
+// conv1_1 weight gradient: dw[64][27] += sum_pixels dy[p][co] * x[p + tap - pad][ci]   (fp32 atomics)
+template <typename T>
+__global__ void __launch_bounds__(256) conv1_1_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+                                                            float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
+                                                            int pad, int nblocks_pix) {
+  __shared__ float sdy[64][65];
+  __shared__ float sx[64][28];
+  const int co = threadIdx.x & 63, kg = threadIdx.x >> 6;  // 4 groups of 7 taps*channels
+  float acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  const long long total = (long long)B * Ho * Wo;
+  for (long long blk = blockIdx.x; blk < nblocks_pix; blk += gridDim.x) {
+    const long long p0 = blk * 64;
+    // stage 64 pixels of dy (coalesced) and their 27 input taps
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+      const int px = i >> 6, c = i & 63;
+      const long long pix = p0 + px;
+      sdy[px][c] = pix < total ? as_float<T>(dy[pix * 64 + c]) : 0.f;
+    }
+    for (int i = threadIdx.x; i < 64 * 27; i += 256) {
+      const int px = i / 27, k = i - px * 27;
+      const long long pix = p0 + px;
+      float v = 0.f;
+      if (pix < total) {
+        const int xo = (int)(pix % Wo), yo = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+        const int tap = k / 3, c = k - tap * 3;
+        const int yi = yo + tap / 3 - pad, xi = xo + tap % 3 - pad;
+        if (yi >= 0 && yi < H && xi >= 0 && xi < W) v = __ldg(x + (((long long)b * 3 + c) * H + yi) * W + xi);
+      }
+      sx[px][k] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int px = 0; px < 64; ++px) {
+      const float d = sdy[px][co];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) acc[j] = fmaf(d, sx[px][kg * 7 + j], acc[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int k = kg * 7 + j;
+    if (k < 27) {
+      const int tap = k / 3, c = k - tap * 3;
+      atomicAdd(dw + co * 27 + c * 9 + tap, acc[j]);  // OIHW
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool2d(2, stride 2, ceil_mode=True) on NHWC, 16-byte channel vectors
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct Vec16 {
+  static constexpr int N = 16 / sizeof(T);
+  T v[N];
+};
+
+template <typename T>
+__global__ void pool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo) {
+  constexpr int VN = 16 / sizeof(T);
+  const int cv = C / VN;
+  const long long total = (long long)B * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    long long r = i / cv;
+    const int xo = (int)(r % Wo);
+    r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float m[VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int y = 2 * yo + dy, x = 2 * xo + dx;
+        if (y < H && x < W) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + (((long long)b * H + y) * W + x) * C) + c);
+          const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+          for (int j = 0; j < VN; ++j) m[j] = fmaxf(m[j], as_float<T>(e[j]));
+        }
+      }
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) oe[j] = from_float<T>(m[j]);  // values are already representable: exact
+    reinterpret_cast<uint4*>(out + (((long long)b * Ho + yo) * Wo + xo) * C)[c] = o;
+  }
+}
+
+// dY[b,y,x,c] = dP[b,y/2,x/2,c] if Y[b,y,x,c] is the FIRST maximum of its window (scan order, like ATen) and > 0 (ReLU)
+template <typename T>
+__global__ void pool_bwd_kernel(const T* __restrict__ yin, const T* __restrict__ dp, T* __restrict__ dy, int B, int H,
+                                int W, int C, int Ho, int Wo, int relu_gate) {
+  constexpr int VN = 16 / sizeof(T);
+  const int cv = C / VN;
+  const long long total = (long long)B * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    long long r = i / cv;
+    const int x = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H);
+    const int b = (int)(r / H);
+    const int yo = y >> 1, xo = x >> 1;
+    const int me = (y & 1) * 2 + (x & 1);
+    float val[4][VN];
+    bool have[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yy = 2 * yo + (q >> 1), xx = 2 * xo + (q & 1);
+      have[q] = yy < H && xx < W;
+      if (have[q]) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(yin + (((long long)b * H + yy) * W + xx) * C) + c);
+        const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) val[q][j] = as_float<T>(e[j]);
+      }
+    }
+    const uint4 gu = __ldg(reinterpret_cast<const uint4*>(dp + (((long long)b * Ho + yo) * Wo + xo) * C) + c);
+    const T* ge = reinterpret_cast<const T*>(&gu);
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      float mine = 0.f;
+      bool win = true;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q == me) mine = val[q][j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q == me || !have[q]) continue;
+        if (q < me ? (val[q][j] >= mine) : (val[q][j] > mine)) win = false;
+      }
+      if (relu_gate && !(mine > 0.f)) win = false;
+      oe[j] = win ? ge[j] : from_float<T>(0.f);
+    }
+    reinterpret_cast<uint4*>(dy + (((long long)b * H + y) * W + x) * C)[c] = o;
+  }
+}
+
+// db[c] += sum over rows of dy[row][c]   (dy row stride ld)
+template <typename T>
+__global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ dy, float* __restrict__ db, long long rows,
+                                                        int C, long long ld, long long rows_per_block) {
+  __shared__ float red[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  for (int cb = 0; cb < C; cb += 64) {
+    const int c = cb + tx;
+    float acc = 0.f;
+    if (c < C)
+      for (long long r = r0 + ty; r < r1; r += 4) acc += as_float<T>(dy[r * ld + c]);
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < C) atomicAdd(db + c, red[0][tx] + red[1][tx] + red[2][tx] + red[3][tx]);
+    __syncthreads();
+  }
+}
+
+// OIHW fp32 -> [O_pad][R*S][I] T   (rows >= O are zero; fp32 values are rounded to tf32)
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int O, int I, int RS, int O_pad) {
+  const long long total = (long long)O_pad * RS * I;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % I);
+    const int rs = (int)((i / I) % RS);
+    const int o = (int)(i / ((long long)I * RS));
+    out[i] = from_float<T>(o < O ? w[((long long)o * I + ci) * RS + rs] : 0.f);
+  }
+}
+// [O_pad][R*S][I] fp32 -> OIHW fp32
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ g, int O, int I, int RS) {
+  const long long total = (long long)O * RS * I;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int rs = (int)(i % RS);
+    const int ci = (int)((i / RS) % I);
+    const int o = (int)(i / ((long long)I * RS));
+    g[i] = dw[((long long)o * RS + rs) * I + ci];
+  }
+}
+
+// Dropout2d(p=0.5) channel multipliers: scale[b][c] in {0, 2}  (counter-based hash RNG)
+__global__ void dropout_scale_kernel(float* __restrict__ scale, int n, unsigned long long seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  scale[i] = (z >> 40) & 1ull ? 2.f : 0.f;
+}
+
+// fp32 NCHW/any -> T elementwise (used for casting small tensors)
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = from_float<T>(in[i]);
+}
+
+static int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace szn
+using namespace szn;
+
+extern "C" const char* szn_last_error(void) { return g_err; }
+extern "C" long long szn_launch_count(void) { return g_launches; }
+extern "C" int szn_abi_version(void) { return 1; }
+
+#define DISPATCH_T(dtype, CALL)                 \
+  do {                                          \
+    if ((dtype) == SZN_BF16) {                  \
+      typedef __nv_bfloat16 T;                  \
+      CALL;                                     \
+    } else if ((dtype) == SZN_F32) {            \
+      typedef float T;                          \
+      CALL;                                     \
+    } else {                                    \
+      return set_error(SZN_ERR_ARG, "bad dtype"); \
+    }                                           \
+  } while (0)
+
+extern "C" int szn_conv1_1_fwd(int dtype, const float* x, const float* w_oihw, const float* bias, void* y, int B, int H,
+                               int W, int pad, void* stream) {
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+  const long long total = (long long)B * Ho * Wo;
+  const unsigned grid = (unsigned)((total + 127) / 128);
+  DISPATCH_T(dtype, (conv1_1_fwd_kernel<T><<<grid, 128, 0, (cudaStream_t)stream>>>(x, w_oihw, bias, (T*)y, B, H, W, Ho, Wo, pad)));
+  return check_launch("szn_conv1_1_fwd");
+}
+
+extern "C" int szn_conv1_1_wgrad(int dtype, const float* x, const void* dy, float* dw_oihw, int B, int H, int W, int pad,
+                                 void* stream) {
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+  const long long total = (long long)B * Ho * Wo;
+  const int nblk = (int)((total + 63) / 64);
+  const int grid = nblk < 148 * 4 ? nblk : 148 * 4;
+  DISPATCH_T(dtype, (conv1_1_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const T*)dy, dw_oihw, B, H, W, Ho, Wo, pad, nblk)));
+  return check_launch("szn_conv1_1_wgrad");
+}
+
+extern "C" int szn_pool_fwd(int dtype, const void* in, void* out, int B, int H, int W, int C, void* stream) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int vn = dtype == SZN_BF16 ? 8 : 4;
+  if (C % vn) return set_error(SZN_ERR_ARG, "szn_pool_fwd: C must be a multiple of 16 bytes");
+  const long long total = (long long)B * Ho * Wo * (C / vn);
+  DISPATCH_T(dtype, (pool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)in, (T*)out, B, H, W, C, Ho, Wo)));
+  return check_launch("szn_pool_fwd");
+}
+
+extern "C" int szn_pool_bwd(int dtype, const void* y, const void* dp, void* dy, int B, int H, int W, int C, int relu_gate,
+                            void* stream) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int vn = dtype == SZN_BF16 ? 8 : 4;
+  if (C % vn) return set_error(SZN_ERR_ARG, "szn_pool_bwd: C must be a multiple of 16 bytes");
+  const long long total = (long long)B * H * W * (C / vn);
+  DISPATCH_T(dtype, (pool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)y, (const T*)dp, (T*)dy, B, H, W, C, Ho, Wo, relu_gate)));
+  return check_launch("szn_pool_bwd");
+}
+
+extern "C" int szn_bias_grad(int dtype, const void* dy, float* db, long long rows, int C, long long ld, void* stream) {
+  long long rpb = (rows + 148 * 8 - 1) / (148 * 8);
+  if (rpb < 64) rpb = 64;
+  const unsigned grid = (unsigned)((rows + rpb - 1) / rpb);
+  DISPATCH_T(dtype, (bias_grad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, db, rows, C, ld, rpb)));
+  return check_launch("szn_bias_grad");
+}
+
+extern "C" int szn_pack_weight(int dtype, const float* w_oihw, void* out, int O, int I, int R, int S, int O_pad,
+                               void* stream) {
+  const long long total = (long long)O_pad * R * S * I;
+  DISPATCH_T(dtype, (pack_weight_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (T*)out, O, I, R * S, O_pad)));
+  return check_launch("szn_pack_weight");
+}
+
+extern "C" int szn_unpack_wgrad(const float* dw_ohwi, float* g_oihw, int O, int I, int R, int S, void* stream) {
+  const long long total = (long long)O * R * S * I;
+  unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dw_ohwi, g_oihw, O, I, R * S);
+  return check_launch("szn_unpack_wgrad");
+}
+
+extern "C" int szn_dropout_scale(float* scale, int n, unsigned long long seed, void* stream) {
+  dropout_scale_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scale, n, seed);
+  return check_launch("szn_dropout_scale");
+}
+
+extern "C" int szn_cast(int dtype, const float* in, void* out, long long n, void* stream) {
+  DISPATCH_T(dtype, (cast_kernel<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, (T*)out, n)));
+  return check_launch("szn_cast");
+}

@@ -1,0 +1,563 @@
+// tcgen05 implicit-GEMM convolution kernels for sm_100a (forward, data-gradient, weight-gradient).
+//
+// One warp-specialised kernel template covers the three GEMM shapes of the VGG16-FCN32s trunk
+// (reference: models.py:43-98 forward, autograd backward of the same layers):
+//
+//   MODE 0  forward   D[pixel, co] = sum_{tap, ci} X[pixel + tap - pad, ci] * Wt[co, tap, ci]
+//           A = activations, K-major (NHWC: channels contiguous), loaded as 4-D TMA boxes
+//               (KC channels x TW x TH pixels) at the tap-shifted coordinate; out-of-image pixels are
+//               zero-filled by TMA, which implements the conv padding (pad=1, and pad=6 of the fc6 dgrad).
+//           B = weights [Cout][taps*Cin], K-major, 2-D TMA boxes.
+//   MODE 1  dgrad     D[pixel, ci] = sum_{tap, co} dY[pixel + pad - tap, co] * Wt[co, tap, ci]
+//           A = dY (K-major), B = the SAME weight buffer read MN-major (ci contiguous), 3-D TMA boxes.
+//   MODE 2  wgrad     D[co, (tap, ci)] = sum_{pixel} dY[pixel, co] * X[pixel + tap - pad, ci]
+//           both operands MN-major (the reduction runs over pixels), split-K over pixel chunks,
+//           fp32 atomics into dW[Cout][taps*Cin].
+//
+// Tiles: UMMA M = 128 (rows = pixels of a TW x TH patch, or output channels for wgrad), N = block_n
+// (32..256), K per stage = 128 bytes of the contraction dim (64 bf16 / 32 tf32), SWIZZLE_128B smem
+// layouts written by TMA and consumed through shared-memory descriptors, fp32 accumulators in TMEM.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM -> regs -> HBM).
+#include "szn_internal.h"
+#include "szn_ptx.cuh"
+
+namespace szn {
+
+struct UmmaParams {
+  int tiles_x, tiles_y, B;  // A-side spatial tiling (M tiles for MODE 0/1, K chunks for MODE 2)
+  int TW, TH;               // tile = TW x TH pixels
+  int H, W;                 // MODE 0/1: extent of the output image
+  int R, S, pad;
+  int Ck;       // MODE 0/1: contraction channels per tap
+  int kchunks;  // ceil(Ck / KC)
+  int N;        // valid GEMM columns
+  int M;        // MODE 2: valid GEMM rows (Cout)
+  int Cin;      // MODE 2: channels per tap inside the N index
+  int block_n, n_tiles, m_tiles, stages, splits, tmem_cols;
+  int zero_smem;
+  void* out;
+  long long ldo;          // row stride of out, elements
+  const float* bias;      // [N] or null
+  const float* scale;     // [B][scale_ld] per-(image, channel) multiplier (Dropout2d) or null
+  int scale_ld;
+  int pix_per_image;      // rows per image for the scale lookup (H*W, or the original H*W when flattened)
+  const void* mask_ref;   // MODE 1: activation whose sign gates the gradient (ReLU backward) or null
+  int relu, out_fp32;
+};
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(192, 1)
+umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaParams p) {
+  constexpr bool TF32 = sizeof(T) == 4;
+  constexpr int KC = 128 / (int)sizeof(T);  // contraction elements per stage
+  constexpr int UK = KC / 4;                // UMMA K (16 bf16 / 8 tf32): 4 MMAs per stage
+  constexpr int A_BYTES = 128 * 128;
+  constexpr bool A_MN = (MODE == 2);
+  constexpr bool B_MN = (MODE != 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  const int block_n = p.block_n;
+  const int stage_bytes = A_BYTES + block_n * 128;
+  const int stages = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty = full + 8;
+  uint64_t* accf = empty + 8;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(accf + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile decode (n fastest so that CTAs sharing an A tile are co-scheduled) ----
+  int idx = blockIdx.x;
+  const int n_tile = idx % p.n_tiles;
+  idx /= p.n_tiles;
+  int m_tile, split = 0;
+  if (MODE == 2) {
+    m_tile = idx % p.m_tiles;
+    split = idx / p.m_tiles;
+  } else {
+    m_tile = idx;
+  }
+  const int n0 = n_tile * block_n;
+
+  int b = 0, x0 = 0, y0 = 0, m0 = 0, n_iters, q_begin = 0;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  if (MODE == 2) {
+    m0 = m_tile * 128;
+    const int total_q = tiles_per_img * p.B;
+    const int per = (total_q + p.splits - 1) / p.splits;
+    q_begin = split * per;
+    int q_end = q_begin + per;
+    if (q_end > total_q) q_end = total_q;
+    n_iters = q_end - q_begin;
+    if (n_iters <= 0) return;  // whole CTA exits together (uniform)
+  } else {
+    b = m_tile / tiles_per_img;
+    const int t = m_tile - b * tiles_per_img;
+    y0 = (t / p.tiles_x) * p.TH;
+    x0 = (t % p.tiles_x) * p.TW;
+    n_iters = p.R * p.S * p.kchunks;
+  }
+
+  if (p.zero_smem) {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = stages * stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(accf, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tptr, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+
+  const int rows_a = p.TW * p.TH;  // rows written by one pixel box
+
+  if (warp == 0 && lane == 0) {
+    // =========================== TMA producer ===========================
+    uint32_t tx;
+    if (MODE == 2) tx = (uint32_t)((128 / KC + block_n / KC) * rows_a * 128);
+    else tx = (uint32_t)(rows_a * 128 + block_n * 128);
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % stages;
+      const uint32_t ph = (uint32_t)(it / stages) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      uint8_t* a_dst = smem + s * stage_bytes;
+      uint8_t* b_dst = a_dst + A_BYTES;
+      mbar_expect_tx(&full[s], tx);
+      if (MODE == 0) {
+        const int tap = it / p.kchunks, cc = it - tap * p.kchunks;
+        const int r = tap / p.S, sx = tap - r * p.S;
+        tma_load_4d(a_dst, &tmA, &full[s], cc * KC, x0 + sx - p.pad, y0 + r - p.pad, b);
+        tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, n0);
+      } else if (MODE == 1) {
+        const int tap = it / p.kchunks, cc = it - tap * p.kchunks;
+        const int r = tap / p.S, sx = tap - r * p.S;
+        tma_load_4d(a_dst, &tmA, &full[s], cc * KC, x0 + p.pad - sx, y0 + p.pad - r, b);
+        for (int g = 0; g < block_n / KC; ++g)
+          tma_load_3d(b_dst + g * KC * 128, &tmB, &full[s], n0 + g * KC, tap, cc * KC);
+      } else {
+        const int q = q_begin + it;
+        const int bb = q / tiles_per_img;
+        const int t = q - bb * tiles_per_img;
+        const int py0 = (t / p.tiles_x) * p.TH, px0 = (t % p.tiles_x) * p.TW;
+        for (int g = 0; g < 128 / KC; ++g)
+          tma_load_4d(a_dst + g * KC * 128, &tmA, &full[s], m0 + g * KC, px0, py0, bb);
+        for (int g = 0; g < block_n / KC; ++g) {
+          const int nn = n0 + g * KC;
+          const int tap = nn / p.Cin, ci0 = nn - tap * p.Cin;
+          const int r = tap / p.S, sx = tap - r * p.S;
+          tma_load_4d(b_dst + g * KC * 128, &tmB, &full[s], ci0, px0 + sx - p.pad, py0 + r - p.pad, bb);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = umma_idesc(TF32 ? 2 : 1, A_MN ? 1 : 0, B_MN ? 1 : 0, 128, block_n);
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % stages;
+      const uint32_t ph = (uint32_t)(it / stages) & 1u;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+      const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // K-major: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzled row.
+        // MN-major: 128 B-wide groups KC*128 B apart (LBO), 8-row K groups 1024 B apart (SBO), K advances UK rows.
+        const uint64_t adesc = A_MN ? umma_desc_sw128(a_addr + k * UK * 128, KC * 128, 1024)
+                                    : umma_desc_sw128(a_addr + k * 32, 16, 1024);
+        const uint64_t bdesc = B_MN ? umma_desc_sw128(b_addr + k * UK * 128, KC * 128, 1024)
+                                    : umma_desc_sw128(b_addr + k * 32, 16, 1024);
+        tc_mma<TF32>(tmem, adesc, bdesc, idesc, (uint32_t)((it | k) != 0));
+      }
+      tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+    }
+    tc_commit(accf);  // accumulator complete
+  } else if (warp >= 2) {
+    // =========================== epilogue ===========================
+    mbar_wait(accf, 0);
+    tc_fence_after();
+    const int q4 = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q4 * 32 + lane;
+    const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16);
+
+    bool ok;
+    size_t orow = 0;  // output row index (pixel or co)
+    int img = 0;
+    if (MODE == 2) {
+      ok = (m0 + row) < p.M;
+      orow = (size_t)(m0 + row);
+    } else {
+      const int ty = row / p.TW, tx_ = row - ty * p.TW;
+      const int y = y0 + ty, x = x0 + tx_;
+      ok = row < rows_a && y < p.H && x < p.W;
+      orow = ((size_t)b * p.H + y) * p.W + x;
+      img = (int)(orow / (size_t)p.pix_per_image);
+    }
+    for (int c0 = 0; c0 < block_n; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tbase + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (!ok) continue;
+      const int nb = n0 + c0;
+      if (nb >= p.N) continue;
+      const int nvalid = (p.N - nb) < 32 ? (p.N - nb) : 32;
+      if (MODE == 2) {
+        float* dst = reinterpret_cast<float*>(p.out) + orow * p.ldo + nb;
+        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 f = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+            atomicAdd(reinterpret_cast<float4*>(dst + j), f);
+          }
+        } else {
+          for (int j = 0; j < nvalid; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+        }
+      } else {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) f[j] += __ldg(p.bias + nb + j);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (p.scale) {
+          const float* sc = p.scale + (size_t)img * p.scale_ld + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) f[j] *= __ldg(sc + j);
+        }
+        if (MODE == 1 && p.mask_ref) {
+          const T* ref = reinterpret_cast<const T*>(p.mask_ref) + orow * p.ldo + nb;
+          if (nvalid == 32) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(ref);
+            if (TF32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 u = __ldg(r4 + j);
+                if (!(__uint_as_float(u.x) > 0.f)) f[4 * j + 0] = 0.f;
+                if (!(__uint_as_float(u.y) > 0.f)) f[4 * j + 1] = 0.f;
+                if (!(__uint_as_float(u.z) > 0.f)) f[4 * j + 2] = 0.f;
+                if (!(__uint_as_float(u.w) > 0.f)) f[4 * j + 3] = 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 u = __ldg(r4 + j);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                  const uint32_t lo = w[e] & 0xFFFFu, hi = w[e] >> 16;
+                  if ((lo & 0x8000u) || (lo & 0x7FFFu) == 0) f[8 * j + 2 * e] = 0.f;
+                  if ((hi & 0x8000u) || (hi & 0x7FFFu) == 0) f[8 * j + 2 * e + 1] = 0.f;
+                }
+              }
+            }
+          } else {
+            for (int j = 0; j < nvalid; ++j)
+              if (!(load_as_float<T>(ref + j) > 0.f)) f[j] = 0.f;
+          }
+        }
+        if (p.out_fp32 || TF32) {
+          float* dst = reinterpret_cast<float*>(p.out) + orow * p.ldo + nb;
+          if (!p.out_fp32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = to_tf32(f[j]);
+          }
+          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            for (int j = 0; j < nvalid; ++j) dst[j] = f[j];
+          }
+        } else {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nb;
+          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0);
+              u.y = *reinterpret_cast<uint32_t*>(&h1);
+              u.z = *reinterpret_cast<uint32_t*>(&h2);
+              u.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(dst + j) = u;
+            }
+          } else {
+            for (int j = 0; j < nvalid; ++j) dst[j] = __float2bfloat16_rn(f[j]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// dims/box innermost first; strides in elements for dims 1..rank-1
+static int make_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const long long* dims,
+                     const long long* strides_elems, const int* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(SZN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const int es = dtype == SZN_BF16 ? 2 : 4;
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], el[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    el[i] = 1;
+    if (i > 0) gs[i - 1] = (cuuint64_t)strides_elems[i] * es;
+  }
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gs[i] % 16) return set_error(SZN_ERR_ARG, "TMA global stride not a multiple of 16 bytes");
+  if (reinterpret_cast<uintptr_t>(base) % 16) return set_error(SZN_ERR_ARG, "TMA base not 16-byte aligned");
+  CUresult r = enc(m, dtype == SZN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                   (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, el, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d) rank %d dims %lld %lld box %d %d", (int)r, rank,
+             dims[0], dims[1], box[0], box[1]);
+    return set_error(SZN_ERR_CUDA, msg);
+  }
+  return 0;
+}
+
+static int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// pick TW x TH (TW*TH <= max_rows) minimising the number of tiles over a W x H image
+static void pick_tile(int W, int H, int max_rows, int* TW, int* TH) {
+  long long best = -1;
+  int bw = max_rows, bh = 1;
+  for (int tw = 1; tw <= max_rows && tw <= 256; ++tw) {
+    int th = max_rows / tw;
+    if (th < 1) break;
+    if (th > 256) th = 256;
+    // only consider the widest useful tiles: powers of two and exact widths
+    const bool pow2 = (tw & (tw - 1)) == 0;
+    if (!pow2 && tw != W && tw != (W + 1) / 2) continue;
+    const long long cnt = (long long)ceil_div(W, tw) * ceil_div(H, th);
+    // prefer fewer tiles, then wider tiles (longer contiguous runs)
+    if (best < 0 || cnt < best || (cnt == best && tw > bw)) {
+      best = cnt;
+      bw = tw;
+      bh = th;
+    }
+  }
+  if (bh > H) bh = H;  // never ask for more rows than exist (keeps the box tight)
+  *TW = bw;
+  *TH = bh;
+}
+
+static int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
+
+template <typename T, int MODE>
+static int launch(const CUtensorMap& a, const CUtensorMap& b, UmmaParams& p, long long grid, cudaStream_t st) {
+  const int stage_bytes = 128 * 128 + p.block_n * 128;
+  // two CTAs per SM when they fit (one's epilogue overlaps the other's main loop)
+  int stages = (110 * 1024) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 3) stages = (220 * 1024) / stage_bytes > 6 ? 6 : (220 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  p.tmem_cols = tmem_cols_for(p.block_n);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(umma_conv_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return set_error(SZN_ERR_CUDA, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  umma_conv_kernel<T, MODE><<<(unsigned)grid, 192, smem, st>>>(a, b, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(SZN_ERR_CUDA, cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+static int pick_block_n(int N, int gran, int maxn) {
+  // largest tile <= maxn (multiple of gran) that minimises padded columns
+  int best = gran, best_waste = 1 << 30;
+  for (int bn = gran; bn <= maxn; bn += gran) {
+    const int tiles = ceil_div(N, bn);
+    const int waste = tiles * bn - N;
+    if (waste < best_waste || (waste == best_waste && bn > best)) {
+      best = bn;
+      best_waste = waste;
+    }
+  }
+  return best;
+}
+
+}  // namespace szn
+
+using namespace szn;
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int szn_conv_fwd(int dtype, const void* x, const void* wt, const float* bias, void* y, int B, int H, int W,
+                            int Cin, int Cout, int R, int S, int pad, int relu, const float* scale, int scale_ld,
+                            int out_fp32, long long ldo, void* stream) {
+  const int KC = dtype == SZN_BF16 ? 64 : 32;
+  if (Cin % KC && !(R == 1 && S == 1)) return set_error(SZN_ERR_ARG, "szn_conv_fwd: Cin must be a multiple of 128 bytes");
+  int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+  if (Ho <= 0 || Wo <= 0) return set_error(SZN_ERR_ARG, "szn_conv_fwd: empty output");
+  UmmaParams p{};
+  p.pix_per_image = Ho * Wo;
+  int Bq = B, Hq = H, Wq = W;
+  if (R == 1 && S == 1 && pad == 0) {  // 1x1: flatten every pixel of the batch into one row of pixels
+    Wq = B * H * W, Hq = 1, Bq = 1, Ho = 1, Wo = Wq;
+  }
+  pick_tile(Wo, Ho, 128, &p.TW, &p.TH);
+  p.tiles_x = ceil_div(Wo, p.TW), p.tiles_y = ceil_div(Ho, p.TH), p.B = Bq;
+  p.H = Ho, p.W = Wo, p.R = R, p.S = S, p.pad = pad, p.Ck = Cin, p.kchunks = ceil_div(Cin, KC);
+  p.N = Cout;
+  p.block_n = pick_block_n(Cout, 32, Cout >= 256 ? 256 : 128);
+  p.n_tiles = ceil_div(Cout, p.block_n);
+  p.out = y, p.ldo = ldo, p.bias = bias, p.scale = scale, p.scale_ld = scale_ld, p.relu = relu, p.out_fp32 = out_fp32;
+  CUtensorMap ta, tb;
+  {
+    long long d[4] = {Cin, Wq, Hq, Bq}, s[4] = {1, Cin, (long long)Wq * Cin, (long long)Hq * Wq * Cin};
+    int bx[4] = {KC, p.TW, p.TH, 1};
+    if (int e = make_tmap(&ta, dtype, x, 4, d, s, bx)) return e;
+    long long K = (long long)R * S * Cin;
+    long long d2[2] = {K, Cout}, s2[2] = {1, K};
+    int bx2[2] = {KC, p.block_n};
+    if (int e = make_tmap(&tb, dtype, wt, 2, d2, s2, bx2)) return e;
+  }
+  const long long grid = (long long)p.tiles_x * p.tiles_y * Bq * p.n_tiles;
+  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 0>(ta, tb, p, grid, (cudaStream_t)stream)
+                           : launch<float, 0>(ta, tb, p, grid, (cudaStream_t)stream);
+}
+
+// dx[B,H,W,Cin] (the conv input's gradient) from dy[B,Ho,Wo,Cout]; optional ReLU gate by `relu_ref` (same shape as dx)
+// and per-(image, channel) multiplier `scale`.
+extern "C" int szn_conv_dgrad(int dtype, const void* dy, const void* wt, void* dx, int B, int H, int W, int Cin,
+                              int Cout, int R, int S, int pad, const void* relu_ref, const float* scale, int scale_ld,
+                              long long ld_dy, void* stream) {
+  const int KC = dtype == SZN_BF16 ? 64 : 32;
+  if (Cin % KC) return set_error(SZN_ERR_ARG, "szn_conv_dgrad: Cin must be a multiple of 128 bytes");
+  int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+  UmmaParams p{};
+  p.pix_per_image = H * W;
+  int Bq = B, Hq = H, Wq = W;
+  if (R == 1 && S == 1 && pad == 0) Wq = B * H * W, Hq = 1, Bq = 1, Ho = 1, Wo = Wq;
+  pick_tile(Wq, Hq, 128, &p.TW, &p.TH);
+  p.tiles_x = ceil_div(Wq, p.TW), p.tiles_y = ceil_div(Hq, p.TH), p.B = Bq;
+  p.H = Hq, p.W = Wq, p.R = R, p.S = S, p.pad = pad, p.Ck = Cout, p.kchunks = ceil_div(Cout, KC);
+  p.N = Cin;
+  p.block_n = pick_block_n(Cin, KC, Cin >= 256 ? 256 : 128);
+  p.n_tiles = ceil_div(Cin, p.block_n);
+  p.out = dx, p.ldo = Cin, p.mask_ref = relu_ref, p.scale = scale, p.scale_ld = scale_ld;
+  CUtensorMap ta, tb;
+  {
+    long long d[4] = {Cout, Wo, Ho, Bq}, s[4] = {1, ld_dy, (long long)Wo * ld_dy, (long long)Ho * Wo * ld_dy};
+    int bx[4] = {KC, p.TW, p.TH, 1};
+    if (int e = make_tmap(&ta, dtype, dy, 4, d, s, bx)) return e;
+    long long d3[3] = {Cin, (long long)R * S, Cout}, s3[3] = {1, Cin, (long long)R * S * Cin};
+    int bx3[3] = {KC, 1, KC};
+    if (int e = make_tmap(&tb, dtype, wt, 3, d3, s3, bx3)) return e;
+  }
+  const long long grid = (long long)p.tiles_x * p.tiles_y * Bq * p.n_tiles;
+  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 1>(ta, tb, p, grid, (cudaStream_t)stream)
+                           : launch<float, 1>(ta, tb, p, grid, (cudaStream_t)stream);
+}
+
+// dw[Cout][R*S*Cin] (fp32, ACCUMULATED into: the caller zeroes it) from x[B,H,W,Cin] and dy[B,Ho,Wo,Cout]
+extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* dw, int B, int H, int W, int Cin,
+                              int Cout, int R, int S, int pad, long long ld_dy, void* stream) {
+  const int KC = dtype == SZN_BF16 ? 64 : 32;
+  if (Cin % KC) return set_error(SZN_ERR_ARG, "szn_conv_wgrad: Cin must be a multiple of 128 bytes");
+  int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+  int Bq = B, Hq = H, Wq = W;
+  if (R == 1 && S == 1 && pad == 0) Wq = B * H * W, Hq = 1, Bq = 1, Ho = 1, Wo = Wq;
+  UmmaParams p{};
+  pick_tile(Wo, Ho, KC, &p.TW, &p.TH);
+  p.tiles_x = ceil_div(Wo, p.TW), p.tiles_y = ceil_div(Ho, p.TH), p.B = Bq;
+  p.R = R, p.S = S, p.pad = pad;
+  p.M = Cout, p.Cin = Cin;
+  p.N = R * S * Cin;
+  p.block_n = pick_block_n(p.N, KC, p.N % 256 == 0 ? 256 : 192);
+  if (p.N % p.block_n) p.block_n = pick_block_n(p.N, KC, 256);
+  p.n_tiles = ceil_div(p.N, p.block_n);
+  p.m_tiles = ceil_div(Cout, 128);
+  const long long total_q = (long long)p.tiles_x * p.tiles_y * Bq;
+  const long long tiles = (long long)p.n_tiles * p.m_tiles;
+  long long splits = (2 * 148 + tiles - 1) / tiles;  // about two waves of CTAs
+  if (splits > total_q / 4) splits = total_q / 4;    // at least 4 chunks per split
+  if (splits < 1) splits = 1;
+  p.splits = (int)splits;
+  p.zero_smem = (p.TW * p.TH < KC) ? 1 : 0;
+  p.out = dw, p.ldo = p.N;
+  CUtensorMap ta, tb;
+  {
+    long long d[4] = {Cout, Wo, Ho, Bq}, s[4] = {1, ld_dy, (long long)Wo * ld_dy, (long long)Ho * Wo * ld_dy};
+    int bx[4] = {KC, p.TW, p.TH, 1};
+    if (int e = make_tmap(&ta, dtype, dy, 4, d, s, bx)) return e;
+    long long d2[4] = {Cin, Wq, Hq, Bq}, s2[4] = {1, Cin, (long long)Wq * Cin, (long long)Hq * Wq * Cin};
+    if (int e = make_tmap(&tb, dtype, x, 4, d2, s2, bx)) return e;
+  }
+  const long long grid = tiles * p.splits;
+  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 2>(ta, tb, p, grid, (cudaStream_t)stream)
+                           : launch<float, 2>(ta, tb, p, grid, (cudaStream_t)stream);
+}

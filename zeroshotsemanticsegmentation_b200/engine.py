@@ -1,0 +1,312 @@
+"""Device-side execution of ``FCN32s.forward`` and its backward through ``libszn.so``.
+
+Follows the reference layer sequence (``models.py:114-160``) and what autograd does for it
+(``trainer_fcn.py:157``), but every device op is one of the hand-written kernels behind the C ABI
+(``include/szn.h``).  PyTorch supplies device memory, the current stream and the autograd hook only.
+
+Data layout in HBM
+  * image ``x``: NCHW fp32 (public API, read once by ``szn_conv1_1_fwd``);
+  * trunk activations: NHWC, element type = precision (``tf32``: fp32 rounded to TF32, ``bf16``);
+  * packed weights ``[Cout][R*S][Cin]`` in the activation type, cached per parameter version;
+  * head: ``s17`` = fp32 ``[B,hs,ws,Dp]`` holding ``score_fr`` (channels 0..D-1) and ``seenmask_score``
+    (channels D, D+1) from ONE GEMM, ``Dp`` = D+2 rounded up to 32;
+  * returned ``f`` (B,D,H,W) / ``s`` (B,2,H,W): NCHW fp32 contiguous, as the reference returns them.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+# (name, Cin, Cout, kernel, pad) or ("poolN",): models.py:43-81
+TRUNK = [
+    ("conv1_1", 3, 64, 3, 100), ("conv1_2", 64, 64, 3, 1), ("pool1",),
+    ("conv2_1", 64, 128, 3, 1), ("conv2_2", 128, 128, 3, 1), ("pool2",),
+    ("conv3_1", 128, 256, 3, 1), ("conv3_2", 256, 256, 3, 1), ("conv3_3", 256, 256, 3, 1), ("pool3",),
+    ("conv4_1", 256, 512, 3, 1), ("conv4_2", 512, 512, 3, 1), ("conv4_3", 512, 512, 3, 1), ("pool4",),
+    ("conv5_1", 512, 512, 3, 1), ("conv5_2", 512, 512, 3, 1), ("conv5_3", 512, 512, 3, 1), ("pool5",),
+]
+CONV_NAMES = [r[0] for r in TRUNK if len(r) == 5] + ["fc6", "fc7"]
+# order of the parameter tensors handed to the autograd function
+PARAM_ORDER = [n + s for n in CONV_NAMES for s in (".weight", ".bias")] + [
+    "score_fr.weight", "score_fr.bias", "seenmask_score.weight", "seenmask_score.bias",
+    "upscore.weight", "seenmask_upscore.weight"]
+
+PRECISIONS = {"tf32": (_lib.F32, torch.float32), "bf16": (_lib.BF16, torch.bfloat16)}
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class PackedWeights:
+    """Per-module cache of kernel-layout weights, refreshed when a parameter's version changes."""
+
+    def __init__(self):
+        self.cache = {}
+
+    def get(self, key, version, build):
+        hit = self.cache.get(key)
+        if hit is not None and hit[0] == version:
+            return hit[1]
+        val = build()
+        self.cache[key] = (version, val)
+        return val
+
+
+def _pack(dt, tdtype, w, o_pad=None):
+    O, I, R, S = w.shape
+    o_pad = O if o_pad is None else o_pad
+    out = torch.empty((o_pad, R * S, I), device=w.device, dtype=tdtype)
+    call("szn_pack_weight", dt, ptr(w), ptr(out), O, I, R, S, o_pad, _lib.stream())
+    return out
+
+
+def is_diag_bilinear(w):
+    """True when ``w`` (Ci,Co,64,64) is exactly what ``_initialize_weights`` wrote (models.py:102-112)."""
+    from .models import bilinear_filter
+    if w.shape[0] != w.shape[1] or w.shape[2] != 64 or w.shape[3] != 64:
+        return False
+    n = w.shape[0]
+    idx = torch.arange(n, device=w.device)
+    diag = w[idx, idx]
+    filt = bilinear_filter(64).to(w.device)
+    if not torch.equal(diag, filt.expand_as(diag)):
+        return False
+    return int(torch.count_nonzero(w)) == int(torch.count_nonzero(diag))
+
+
+class FCN32sFunction(torch.autograd.Function):
+    """(x, *params) -> (f, s); both heads are always evaluated (models.py:145-151)."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        dt, tdtype = PRECISIONS[module.precision]
+        st = _lib.stream()
+        dev = x.device
+        if x.dtype != torch.float32:
+            raise TypeError("FCN32s expects an fp32 image batch")
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        P = dict(zip(PARAM_ORDER, params))
+        D = P["score_fr.weight"].shape[0]
+        Dp = round_up(D + 2, 32)
+        pw = module._packed
+
+        def packed(name, o_pad=None):
+            w = P[name + ".weight"]
+            return pw.get((name, dt), (w._version, w.data_ptr()), lambda: _pack(dt, tdtype, w.detach(), o_pad))
+
+        acts = {}   # name -> NHWC activation (post-ReLU / pooled)
+        dims = {}   # name -> (H, W, C) of that activation
+        # conv1_1 on CUDA cores straight from the NCHW image
+        h, w_ = H + 198, W + 198
+        a = torch.empty((B, h, w_, 64), device=dev, dtype=tdtype)
+        call("szn_conv1_1_fwd", dt, ptr(x), ptr(P["conv1_1.weight"].detach().contiguous()),
+             ptr(P["conv1_1.bias"].detach()), ptr(a), B, H, W, 100, st)
+        acts["conv1_1"], dims["conv1_1"] = a, (h, w_, 64)
+        c = 64
+        for row in TRUNK[1:]:
+            name = row[0]
+            if len(row) == 1:
+                ho, wo = (h + 1) // 2, (w_ + 1) // 2
+                o = torch.empty((B, ho, wo, c), device=dev, dtype=tdtype)
+                call("szn_pool_fwd", dt, ptr(a), ptr(o), B, h, w_, c, st)
+                h, w_ = ho, wo
+            else:
+                _, cin, cout, k, pad = row
+                o = torch.empty((B, h, w_, cout), device=dev, dtype=tdtype)
+                call("szn_conv_fwd", dt, ptr(a), ptr(packed(name)), ptr(P[name + ".bias"].detach()), ptr(o),
+                     B, h, w_, cin, cout, k, k, pad, 1, None, 0, 0, cout, st)
+                c = cout
+            a = o
+            acts[name], dims[name] = a, (h, w_, c)
+        # fc6 (7x7 valid) / fc7 (1x1) with ReLU and Dropout2d folded into the epilogue
+        training = module.training
+        drop = None
+        if training:
+            drop = torch.empty((2, B, 4096), device=dev, dtype=torch.float32)
+            if module._forced_drop_masks is not None:
+                m6, m7 = module._forced_drop_masks
+                drop[0].copy_(m6.to(dev).float() * 2.0)
+                drop[1].copy_(m7.to(dev).float() * 2.0)
+            else:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+                call("szn_dropout_scale", ptr(drop), 2 * B * 4096, seed, st)
+        hs, ws = h - 6, w_ - 6
+        h6 = torch.empty((B, hs, ws, 4096), device=dev, dtype=tdtype)
+        call("szn_conv_fwd", dt, ptr(a), ptr(packed("fc6")), ptr(P["fc6.bias"].detach()), ptr(h6), B, h, w_, 512, 4096,
+             7, 7, 0, 1, ptr(drop[0]) if training else None, 4096, 0, 4096, st)
+        h7 = torch.empty((B, hs, ws, 4096), device=dev, dtype=tdtype)
+        call("szn_conv_fwd", dt, ptr(h6), ptr(packed("fc7")), ptr(P["fc7.bias"].detach()), ptr(h7), B, hs, ws, 4096,
+             4096, 1, 1, 0, 1, ptr(drop[1]) if training else None, 4096, 0, 4096, st)
+        # score_fr and seenmask_score as ONE GEMM with N = D + 2 (padded to Dp)
+        wf, ws_ = P["score_fr.weight"], P["seenmask_score.weight"]
+
+        def build_head():
+            cat = torch.cat([wf.detach(), ws_.detach()], 0).contiguous()
+            bias = torch.zeros(Dp, device=dev, dtype=torch.float32)
+            bias[:D] = P["score_fr.bias"].detach()
+            bias[D:D + 2] = P["seenmask_score.bias"].detach()
+            return _pack(dt, tdtype, cat, Dp), bias
+
+        head_w, head_b = pw.get(("head", dt), (wf._version, ws_._version, P["score_fr.bias"]._version,
+                                                P["seenmask_score.bias"]._version, wf.data_ptr()), build_head)
+        s17 = torch.empty((B, hs, ws, Dp), device=dev, dtype=torch.float32)
+        call("szn_conv_fwd", dt, ptr(h7), ptr(head_w), ptr(head_b), ptr(s17), B, hs, ws, 4096, Dp, 1, 1, 0, 0,
+             None, 0, 1, Dp, st)
+        # upscore (x32 bilinear + crop 19) and the dense 2-channel seenmask_upscore
+        up_w, sm_up_w = P["upscore.weight"], P["seenmask_upscore.weight"]
+        diag = pw.get(("upscore_diag",), (up_w._version, up_w.data_ptr()), lambda: is_diag_bilinear(up_w.detach()))
+        f = torch.empty((B, D, H, W), device=dev, dtype=torch.float32)
+        if diag:
+            call("szn_upsample32_crop_fwd", ptr(s17), ptr(f), B, D, H, W, hs, ws, Dp, 0, st)
+        else:
+            call("szn_deconv_small_fwd", ptr(s17), ptr(up_w.detach().contiguous()), ptr(f), B, D, D, H, W, hs, ws,
+                 Dp, 0, st)
+        s = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+        call("szn_deconv_small_fwd", ptr(s17), ptr(sm_up_w.detach().contiguous()), ptr(s), B, 2, 2, H, W, hs, ws,
+             Dp, D, st)
+
+        ctx.module = module
+        ctx.saved = dict(x=x, acts=acts, dims=dims, h6=h6, h7=h7, s17=s17, drop=drop, P=P, head_w=head_w,
+                         geom=(B, H, W, D, Dp, hs, ws), diag=diag, dt=dt, tdtype=tdtype)
+        return f, s
+
+    @staticmethod
+    def backward(ctx, gf, gs):
+        sv = ctx.saved
+        module = ctx.module
+        dt, tdtype = sv["dt"], sv["tdtype"]
+        st = _lib.stream()
+        B, H, W, D, Dp, hs, ws = sv["geom"]
+        P, acts, dims = sv["P"], sv["acts"], sv["dims"]
+        dev = sv["x"].device
+        pw = module._packed
+        need = {n: g for n, g in zip(PARAM_ORDER, ctx.needs_input_grad[2:])}
+        grads = {n: None for n in PARAM_ORDER}
+
+        def packed(name):
+            return pw.cache[(name, dt)][1]
+
+        def zeros(shape, dtype=torch.float32):
+            return torch.zeros(shape, device=dev, dtype=dtype)
+
+        # ---------------- heads: d s17 ----------------
+        ds17 = zeros((B, hs, ws, Dp), tdtype)
+        if gf is not None:
+            gf = gf.contiguous()
+            if sv["diag"]:
+                call("szn_upsample32_crop_bwd", dt, ptr(gf), ptr(ds17), B, D, H, W, hs, ws, Dp, 0, st)
+            else:
+                call("szn_deconv_small_dgrad", dt, ptr(gf), ptr(P["upscore.weight"].detach().contiguous()), ptr(ds17),
+                     B, D, D, H, W, hs, ws, Dp, 0, st)
+            if need["upscore.weight"] and module.upscore_weight_grad:
+                g = torch.empty_like(P["upscore.weight"])
+                call("szn_deconv_small_wgrad", ptr(sv["s17"]), ptr(gf), ptr(g), B, D, D, H, W, hs, ws, Dp, 0, st)
+                grads["upscore.weight"] = g
+        if gs is not None:
+            gs = gs.contiguous()
+            call("szn_deconv_small_dgrad", dt, ptr(gs), ptr(P["seenmask_upscore.weight"].detach().contiguous()),
+                 ptr(ds17), B, 2, 2, H, W, hs, ws, Dp, D, st)
+            if need["seenmask_upscore.weight"]:
+                g = torch.empty_like(P["seenmask_upscore.weight"])
+                call("szn_deconv_small_wgrad", ptr(sv["s17"]), ptr(gs), ptr(g), B, 2, 2, H, W, hs, ws, Dp, D, st)
+                grads["seenmask_upscore.weight"] = g
+
+        # which trunk layers still need a data gradient flowing into them
+        trunk_need = [need[n + ".weight"] or need[n + ".bias"] for n in CONV_NAMES]
+        first_needed = next((i for i, v in enumerate(trunk_need) if v), None)
+
+        # ---------------- score heads: wgrad / bias / dgrad ----------------
+        rows17 = B * hs * ws
+        if any(need[k] for k in ("score_fr.weight", "seenmask_score.weight")):
+            dwh = zeros((Dp, 4096))
+            call("szn_conv_wgrad", dt, ptr(sv["h7"]), ptr(ds17), ptr(dwh), B, hs, ws, 4096, Dp, 1, 1, 0, Dp, st)
+            if need["score_fr.weight"]:
+                grads["score_fr.weight"] = dwh[:D].reshape(D, 4096, 1, 1)
+            if need["seenmask_score.weight"]:
+                grads["seenmask_score.weight"] = dwh[D:D + 2].reshape(2, 4096, 1, 1)
+        if any(need[k] for k in ("score_fr.bias", "seenmask_score.bias")):
+            dbh = zeros((Dp,))
+            call("szn_bias_grad", dt, ptr(ds17), ptr(dbh), rows17, Dp, Dp, st)
+            if need["score_fr.bias"]:
+                grads["score_fr.bias"] = dbh[:D]
+            if need["seenmask_score.bias"]:
+                grads["seenmask_score.bias"] = dbh[D:D + 2]
+        if first_needed is None:
+            return (None, None) + tuple(grads[n] for n in PARAM_ORDER)
+
+        drop = sv["drop"]
+        d7 = torch.empty((B, hs, ws, 4096), device=dev, dtype=tdtype)
+        call("szn_conv_dgrad", dt, ptr(ds17), ptr(sv["head_w"]), ptr(d7), B, hs, ws, 4096, Dp, 1, 1, 0,
+             ptr(sv["h7"]), ptr(drop[1]) if drop is not None else None, 4096, Dp, st)
+
+        def conv_backward(name, x_act, dy, xh, xw, cin, cout, k, pad, want_dx, relu_ref, scale=None):
+            """wgrad + bias grad of one conv, then (optionally) its data gradient."""
+            ho, wo = xh + 2 * pad - k + 1, xw + 2 * pad - k + 1
+            if need[name + ".weight"]:
+                dw = zeros((cout, k * k, cin))
+                call("szn_conv_wgrad", dt, ptr(x_act), ptr(dy), ptr(dw), B, xh, xw, cin, cout, k, k, pad, cout, st)
+                if k == 1:
+                    grads[name + ".weight"] = dw.reshape(cout, cin, 1, 1)
+                else:
+                    g = torch.empty((cout, cin, k, k), device=dev, dtype=torch.float32)
+                    call("szn_unpack_wgrad", ptr(dw), ptr(g), cout, cin, k, k, st)
+                    grads[name + ".weight"] = g
+            if need[name + ".bias"]:
+                db = zeros((cout,))
+                call("szn_bias_grad", dt, ptr(dy), ptr(db), B * ho * wo, cout, cout, st)
+                grads[name + ".bias"] = db
+            if not want_dx:
+                return None
+            dx = torch.empty((B, xh, xw, cin), device=dev, dtype=tdtype)
+            call("szn_conv_dgrad", dt, ptr(dy), ptr(packed(name)), ptr(dx), B, xh, xw, cin, cout, k, k, pad,
+                 ptr(relu_ref), ptr(scale), 4096 if scale is not None else 0, cout, st)
+            return dx
+
+        n_convs = len(CONV_NAMES)
+        # fc7 (index n_convs-1), fc6 (n_convs-2)
+        h5, w5, _ = dims["pool5"]
+        d6 = conv_backward("fc7", sv["h6"], d7, hs, ws, 4096, 4096, 1, 0, first_needed <= n_convs - 2, sv["h6"],
+                           drop[0] if drop is not None else None)
+        del d7
+        if d6 is None:
+            return (None, None) + tuple(grads[n] for n in PARAM_ORDER)
+        g = conv_backward("fc6", acts["pool5"], d6, h5, w5, 512, 4096, 7, 0, first_needed <= n_convs - 3, None)
+        del d6
+        # walk the trunk backwards
+        rows = TRUNK
+        i = len(rows) - 1
+        while i >= 0 and g is not None:
+            row = rows[i]
+            if len(row) == 1:
+                # g = d(pool out); route to the pre-pool activation (the previous conv's ReLU output)
+                prev = rows[i - 1][0]
+                ph, pw_, pc = dims[prev]
+                dy = torch.empty((B, ph, pw_, pc), device=dev, dtype=tdtype)
+                call("szn_pool_bwd", dt, ptr(acts[prev]), ptr(g), ptr(dy), B, ph, pw_, pc, 1, st)
+                g = dy
+            else:
+                name, cin, cout, k, pad = row
+                ci = CONV_NAMES.index(name)
+                if name == "conv1_1":
+                    if need["conv1_1.weight"]:
+                        dw = zeros((64, 3, 3, 3))
+                        call("szn_conv1_1_wgrad", dt, ptr(sv["x"]), ptr(g), ptr(dw), B, H, W, 100, st)
+                        grads["conv1_1.weight"] = dw
+                    if need["conv1_1.bias"]:
+                        db = zeros((64,))
+                        xh, xw, _ = dims["conv1_1"]
+                        call("szn_bias_grad", dt, ptr(g), ptr(db), B * xh * xw, 64, 64, st)
+                        grads["conv1_1.bias"] = db
+                    g = None
+                else:
+                    prev = rows[i - 1][0]
+                    xh, xw, _ = dims[prev]
+                    prev_is_pool = len(rows[i - 1]) == 1
+                    g = conv_backward(name, acts[prev], g, xh, xw, cin, cout, k, pad, first_needed < ci,
+                                      None if prev_is_pool else acts[prev])
+            i -= 1
+        return (None, None) + tuple(grads[n] for n in PARAM_ORDER)

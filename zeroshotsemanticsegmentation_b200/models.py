@@ -1,0 +1,110 @@
+"""Drop-in for the reference's ``models.py``: ``FCN32s`` with the same constructor, attribute names,
+``state_dict`` keys/shapes and ``forward(x, mode)`` contract (``models.py:27-160``), executed by the
+sm_100a kernels of ``libszn.so``.  There is no CPU / eager fallback.
+
+Sub-modules are real ``nn.Conv2d`` / ``nn.ConvTranspose2d`` / ``nn.ReLU`` / ``nn.MaxPool2d`` /
+``nn.Dropout2d`` instances so that ``train.py:get_parameters`` (``train.py:302-331``),
+``copy_params_from_vgg16`` and checkpoint loading work unchanged; they only hold parameters —
+``forward`` never calls them.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine
+
+
+def bilinear_filter(kernel_size: int = 64) -> torch.Tensor:
+    """2-D tent filter used for the upsampling deconvs (reference ``get_upsampling_weight``, models.py:11-19)."""
+    factor = (kernel_size + 1) // 2
+    center = factor - 1 if kernel_size % 2 == 1 else factor - 0.5
+    k = np.arange(kernel_size, dtype=np.float64)
+    w1 = 1.0 - np.abs(k - center) / factor
+    return torch.from_numpy(w1[:, None] * w1[None, :]).float()
+
+
+def get_upsampling_weight(in_channels, out_channels, kernel_size):
+    """(in,out,k,k) weight with the bilinear filter on the channel diagonal (models.py:11-24)."""
+    w = torch.zeros(in_channels, out_channels, kernel_size, kernel_size)
+    n = min(in_channels, out_channels)
+    idx = torch.arange(n)
+    w[idx, idx] = bilinear_filter(kernel_size)
+    return w
+
+
+class FCN32s(nn.Module):
+    """VGG16-FCN32s with an embedding head (``score_fr``/``upscore``) and a seen-mask head
+    (``seenmask_score``/``seenmask_upscore``), reference ``models.py:27-160``.
+
+    Extra keyword arguments (not in the reference):
+      precision: ``"tf32"`` (fp32 storage, TF32 tensor-core products; meets the 1e-3 forward tolerance)
+                 or ``"bf16"`` (bf16 storage and products, fp32 accumulate).
+      upscore_weight_grad: also compute the dense ``upscore.weight.grad`` (213 GFLOP/image at D=300 for a
+                 weight the reference never optimises, ``train.py:324-327``); off by default.
+    """
+
+    def __init__(self, n_class=21, precision="tf32", upscore_weight_grad=False):
+        super().__init__()
+        if precision not in engine.PRECISIONS:
+            raise ValueError("precision must be one of %s" % list(engine.PRECISIONS))
+        self.precision = precision
+        self.upscore_weight_grad = upscore_weight_grad
+        for row in engine.TRUNK:
+            if len(row) == 1:
+                setattr(self, row[0], nn.MaxPool2d(2, stride=2, ceil_mode=True))
+            else:
+                name, cin, cout, k, pad = row
+                setattr(self, name, nn.Conv2d(cin, cout, k, padding=pad))
+                setattr(self, name.replace("conv", "relu"), nn.ReLU(inplace=True))
+        self.fc6 = nn.Conv2d(512, 4096, 7)
+        self.relu6 = nn.ReLU(inplace=True)
+        self.drop6 = nn.Dropout2d()
+        self.fc7 = nn.Conv2d(4096, 4096, 1)
+        self.relu7 = nn.ReLU(inplace=True)
+        self.drop7 = nn.Dropout2d()
+        self.score_fr = nn.Conv2d(4096, n_class, 1)
+        self.upscore = nn.ConvTranspose2d(n_class, n_class, 64, stride=32, bias=False)
+        self.seenmask_score = nn.Conv2d(4096, 2, 1)
+        self.seenmask_upscore = nn.ConvTranspose2d(2, 2, 64, stride=32, bias=False)
+        self._initialize_weights()
+        self._packed = engine.PackedWeights()
+        self._forced_drop_masks = None  # tests inject Dropout2d masks here: (m6, m7), each (B,4096) in {0,1}
+
+    def _initialize_weights(self):
+        # convs keep torch's default init (the zero-init is commented out upstream, models.py:104-108)
+        for m in self.modules():
+            if isinstance(m, nn.ConvTranspose2d):
+                assert m.kernel_size[0] == m.kernel_size[1]
+                with torch.no_grad():
+                    m.weight.copy_(get_upsampling_weight(m.in_channels, m.out_channels, m.kernel_size[0]))
+
+    def _ordered_params(self):
+        sd = dict(self.named_parameters())
+        return [sd[n] for n in engine.PARAM_ORDER]
+
+    def forward(self, x, mode="fcn"):
+        if mode not in ("fcn", "seenmask", "both"):
+            raise Exception("model given unexpected forward mode")
+        if not x.is_cuda:
+            raise RuntimeError("FCN32s (B200 build) runs on CUDA only: move the model and input to the GPU")
+        f, s = engine.FCN32sFunction.apply(self, x, *self._ordered_params())
+        if mode == "fcn":
+            return f
+        if mode == "seenmask":
+            return s
+        return f, s
+
+    def copy_params_from_vgg16(self, vgg16):
+        """models.py:162-193: conv weights from ``vgg16.features``, fc6/fc7 from ``classifier[0|3]``."""
+        mine = [getattr(self, r[0]) for r in engine.TRUNK if len(r) == 5]
+        theirs = [m for m in vgg16.features if isinstance(m, nn.Conv2d)]
+        for src, dst in zip(theirs, mine):
+            assert src.weight.size() == dst.weight.size() and src.bias.size() == dst.bias.size()
+            dst.weight.data = src.weight.data
+            dst.bias.data = src.bias.data
+        for i, name in zip([0, 3], ["fc6", "fc7"]):
+            src, dst = vgg16.classifier[i], getattr(self, name)
+            dst.weight.data = src.weight.data.view(dst.weight.size())
+            dst.bias.data = src.bias.data.view(dst.bias.size())

@@ -1,0 +1,206 @@
+"""Drop-in for the hot-path functions of the reference's ``utils.py``: same names, argument meaning
+and return types (``utils.py:19-102`` losses, ``utils.py:159-205`` inference), executed by fused
+sm_100a kernels.  Differences, all supersets of the reference behaviour:
+
+* ``cosine_loss`` / ``infer_lbl*`` accept any batch size (the reference is only correct for n == 1,
+  SURVEY §0.4); for n == 1 the result is the reference's.
+* the embedding losses also accept ``target_embed=None, table=E``: the per-pixel target vector is then
+  gathered from the (C, D) class table on the device (what the datasets do on the host,
+  ``pascal_dataset.py:122-128``), which avoids materialising / uploading the (n, D, h, w) target.
+* ``accum_hook`` (a callable applied in place to the device accumulator ``[sum, n_valid]`` before the loss is
+  formed, e.g. ``torch.distributed.all_reduce``) lets data-parallel training normalise by the GLOBAL valid count.
+
+There is no CPU fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import pickle
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+
+def load_obj(name):
+    """utils.py:11-13."""
+    with open(name + ".pkl", "rb") as f:
+        return pickle.load(f, encoding="latin-1")
+
+
+def save_obj(obj, name):
+    """utils.py:15-17."""
+    with open(name + ".pkl", "wb") as f:
+        pickle.dump(obj, f, pickle.HIGHEST_PROTOCOL)
+
+
+def _check_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("zeroshotsemanticsegmentation_b200.utils runs on CUDA tensors only (no CPU fallback)")
+
+
+def _as_f32(t):
+    return t.detach().contiguous().float() if t is not None else None
+
+
+class _EmbedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, score, target, target_embed, table, kind, accum_hook):
+        _check_cuda(score, target, target_embed, table)
+        n, c, h, w = score.shape
+        sc = _as_f32(score)
+        tg = target.detach().contiguous().long()
+        te, tb = _as_f32(target_embed), _as_f32(table)
+        dev = score.device
+        stats = torch.empty((n * h * w * 3,), device=dev, dtype=torch.float32) if kind == 0 else None
+        accum = torch.empty(2, device=dev, dtype=torch.float64)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        st = _lib.stream()
+        call("szn_embed_loss_fwd", kind, ptr(sc), ptr(tg), ptr(te), ptr(tb), n, c, h, w, ptr(stats), ptr(accum),
+             ptr(loss), st)
+        if accum_hook is not None:  # e.g. all-reduce of {sum, n_valid} across data-parallel ranks
+            accum_hook(accum)
+            call("szn_loss_finalize", kind, ptr(accum), ptr(loss), st)
+        ctx.saved = (sc, tg, te, tb, stats, accum, kind)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        sc, tg, te, tb, stats, accum, kind = ctx.saved
+        n, c, h, w = sc.shape
+        g = torch.empty_like(sc)
+        go = gout.detach().contiguous().float()
+        call("szn_embed_loss_bwd", kind, ptr(sc), ptr(tg), ptr(te), ptr(tb), n, c, h, w, ptr(stats), ptr(accum),
+             ptr(go), ptr(g), _lib.stream())
+        return g, None, None, None, None, None
+
+
+class _CrossEntropy2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, score, target, size_average):
+        _check_cuda(score, target)
+        n, c, h, w = score.shape
+        sc = _as_f32(score)
+        tg = target.detach().contiguous().long()
+        dev = score.device
+        lse = torch.empty((n * h * w,), device=dev, dtype=torch.float32)
+        accum = torch.empty(2, device=dev, dtype=torch.float64)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        call("szn_ce2d_fwd", ptr(sc), ptr(tg), n, c, h, w, int(bool(size_average)), ptr(lse), ptr(accum), ptr(loss),
+             _lib.stream())
+        ctx.saved = (sc, tg, lse, accum, int(bool(size_average)))
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        sc, tg, lse, accum, sa = ctx.saved
+        n, c, h, w = sc.shape
+        g = torch.empty_like(sc)
+        go = gout.detach().contiguous().float()
+        call("szn_ce2d_bwd", ptr(sc), ptr(tg), n, c, h, w, sa, ptr(lse), ptr(accum), ptr(go), ptr(g), _lib.stream())
+        return g, None, None
+
+
+def cross_entropy2d(score, target, weight=None, size_average=False):
+    """Per-pixel softmax cross entropy, summed over ``target >= 0`` (``utils.py:19-48``).
+    score (n,c,h,w), target (n,h,w) int64; ``size_average`` divides by the number of valid pixels."""
+    if weight is not None:
+        raise NotImplementedError("class weights are never passed by the reference trainers")
+    return _CrossEntropy2d.apply(score, target, size_average)
+
+
+def mse_loss(score, target, target_embed=None, table=None, accum_hook=None):
+    """sum over valid pixels and channels of (score - target_embed)^2 / n_valid (``utils.py:50-73``)."""
+    return _EmbedLoss.apply(score, target, target_embed, table, 1, accum_hook)
+
+
+def cosine_loss(score, target, target_embed=None, table=None, accum_hook=None):
+    """(N - sum_valid cos(score_p, target_embed_p)) / N (``utils.py:75-102``)."""
+    return _EmbedLoss.apply(score, target, target_embed, table, 0, accum_hook)
+
+
+def _labels_device(score, embed_arr):
+    _check_cuda(score, embed_arr)
+    n, c, h, w = score.shape
+    sc, tb = _as_f32(score), _as_f32(embed_arr)
+    C, D = tb.shape
+    if D != c:
+        raise ValueError("embedding width %d does not match score channels %d" % (D, c))
+    en = torch.empty(C, device=score.device, dtype=torch.float32)
+    out = torch.empty((n, h, w), device=score.device, dtype=torch.int64)
+    call("szn_embed_argmax", ptr(sc), ptr(tb), n, c, h, w, C, ptr(en), ptr(out), _lib.stream())
+    return out
+
+
+def infer_lbl(score, embed_arr, cuda=True):
+    """Nearest class embedding by cosine similarity, zero rows score 0 (``utils.py:159-185``).
+    Returns an ``np.ndarray`` (n,h,w) int64 like the reference."""
+    return _labels_device(score, embed_arr).cpu().numpy()
+
+
+def _stitch(score, seen_embed_arr, unseen_embed_arr, seen_mask_score=None, target=None, unseen=None):
+    seen_lbl = _labels_device(score, seen_embed_arr)
+    unseen_lbl = _labels_device(score, unseen_embed_arr)
+    n, h, w = seen_lbl.shape
+    out = torch.empty_like(seen_lbl)
+    sm = _as_f32(seen_mask_score)
+    tg = target.detach().contiguous().long() if target is not None else None
+    un = torch.as_tensor(list(unseen), device=score.device, dtype=torch.int64) if unseen is not None else None
+    call("szn_stitch_labels", ptr(seen_lbl), ptr(unseen_lbl), ptr(sm), ptr(tg), ptr(un),
+         0 if un is None else un.numel(), n, h, w, ptr(out), _lib.stream())
+    return out
+
+
+def infer_lbl_forced_unseen(score, target, seen_embed_arr, unseen_embed_arr, unseen, cuda=True):
+    """``utils.py:188-192``: pixels whose ground truth is an unseen class are labelled among unseen classes only."""
+    _check_cuda(target)
+    return _stitch(score, seen_embed_arr, unseen_embed_arr, target=target, unseen=unseen).cpu().numpy()
+
+
+def infer_lbl_szn(score, seen_mask_score, seen_embed_arr, unseen_embed_arr, cuda=True):
+    """``utils.py:195-199``: the seen-mask head decides per pixel which table is used."""
+    _check_cuda(seen_mask_score)
+    return _stitch(score, seen_embed_arr, unseen_embed_arr, seen_mask_score=seen_mask_score).cpu().numpy()
+
+
+def stich_seen_unseen_with_mask(score, seen_embed_arr, unseen_embed_arr, unseen_mask, cuda=True):
+    """``utils.py:201-205`` with an explicit boolean mask (n,h,w)."""
+    pred = infer_lbl(score, seen_embed_arr)
+    alt = infer_lbl(score, unseen_embed_arr)
+    pred[unseen_mask] = alt[unseen_mask]
+    return pred
+
+
+# ---- host-side metrics (utils.py:104-154); device version is SURVEY §8f row 1 ----
+
+def _fast_hist(label_true, label_pred, n_class, target="all", unseen=None):
+    keep = (label_true >= 0) & (label_true < n_class)
+    if target == "unseen":
+        keep &= np.isin(label_true, unseen)
+    elif target == "seen":
+        keep &= np.isin(label_true, [c for c in range(n_class) if c not in unseen])
+    idx = n_class * label_true[keep].astype(int) + label_pred[keep]
+    return np.bincount(idx, minlength=n_class ** 2).reshape(n_class, n_class)
+
+
+def _hist_to_metrics(hist):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tp = np.diag(hist)
+        acc = tp.sum() / hist.sum()
+        acc_cls = np.nanmean(tp / hist.sum(axis=1))
+        iu = tp / (hist.sum(axis=1) + hist.sum(axis=0) - tp)
+        freq = hist.sum(axis=1) / hist.sum()
+        return acc, acc_cls, np.nanmean(iu), (freq[freq > 0] * iu[freq > 0]).sum()
+
+
+def label_accuracy_score(label_trues, label_preds, n_class, unseen=None):
+    """Pixel accuracy, mean class accuracy, mean IU, frequency-weighted IU (``utils.py:133-154``)."""
+    kinds = ["all"] + (["seen", "unseen"] if unseen else [])
+    hists = {k: np.zeros((n_class, n_class)) for k in kinds}
+    for lt, lp in zip(label_trues, label_preds):
+        for k in kinds:
+            hists[k] += _fast_hist(lt.flatten(), lp.flatten(), n_class, target=k, unseen=unseen)
+    res = [_hist_to_metrics(hists[k]) for k in kinds]
+    return res[0] if not unseen else tuple(res)
