@@ -61,6 +61,23 @@ def st():
     return torch.cuda.current_stream().cuda_stream
 
 
+_KEEP = []
+
+
+def dp(t):
+    """Device pointer of a tensor that is kept alive until the test ends (a temporary would be freed -- and its
+    block reused by the next allocation -- before the kernel that reads it has even been enqueued)."""
+    _KEEP.append(t)
+    return t.data_ptr()
+
+
+@pytest.fixture(autouse=True)
+def _release_after_test():
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
 CONV_CASES = [
     # B, H, W, Cin, Cout, k, pad
     (2, 20, 37, 64, 64, 3, 1),
@@ -85,8 +102,8 @@ def test_conv_fwd(prec, case):
     Ho, Wo = ref.shape[2:]
     y = torch.full((B, Ho, Wo, Cout), float("nan"), device=DEV, dtype=tdtype(prec))
     L = lib()
-    L.call("szn_conv_fwd", dcode(prec), nhwc(x, prec).data_ptr(), ohwi(w, prec).data_ptr(), b.to(DEV).data_ptr(),
-           y.data_ptr(), B, H, W, Cin, Cout, k, k, pad, 1, scale.to(DEV).data_ptr(), Cout, 0, Cout, st())
+    L.call("szn_conv_fwd", dcode(prec), dp(nhwc(x, prec)), dp(ohwi(w, prec)), dp(b.to(DEV)),
+           dp(y), B, H, W, Cin, Cout, k, k, pad, 1, dp(scale.to(DEV)), Cout, 0, Cout, st())
     torch.cuda.synchronize()
     got = from_nhwc(y)
     tol = 1e-3 if prec == "tf32" else 1e-2  # the kernel rounds its output to the storage type
@@ -105,8 +122,8 @@ def test_conv_fwd_fp32_out_no_relu(prec):
     ref = F.conv2d(x, w, b[:Cout - 10])
     y = torch.full((B, H, W, Cout), float("nan"), device=DEV, dtype=torch.float32)
     L = lib()
-    L.call("szn_conv_fwd", dcode(prec), nhwc(x, prec).data_ptr(), ohwi(w, prec, Cout).data_ptr(), b.to(DEV).data_ptr(),
-           y.data_ptr(), B, H, W, Cin, Cout, 1, 1, 0, 0, None, 0, 1, Cout, st())
+    L.call("szn_conv_fwd", dcode(prec), dp(nhwc(x, prec)), dp(ohwi(w, prec, Cout)), dp(b.to(DEV)),
+           dp(y), B, H, W, Cin, Cout, 1, 1, 0, 0, None, 0, 1, Cout, st())
     torch.cuda.synchronize()
     got = from_nhwc(y)
     assert relerr(got[:, :Cout - 10], ref) < 1e-5
@@ -130,8 +147,8 @@ def test_conv_dgrad(prec, case):
     ref = dx * scale[:, :, None, None] * (ref_act > 0)
     out = torch.full((B, H, W, Cin), float("nan"), device=DEV, dtype=tdtype(prec))
     L = lib()
-    L.call("szn_conv_dgrad", dcode(prec), nhwc(dy, prec).data_ptr(), ohwi(w, prec).data_ptr(), out.data_ptr(), B, H, W,
-           Cin, Cout, k, k, pad, nhwc(ref_act, prec).data_ptr(), scale.to(DEV).data_ptr(), Cin, Cout, st())
+    L.call("szn_conv_dgrad", dcode(prec), dp(nhwc(dy, prec)), dp(ohwi(w, prec)), dp(out), B, H, W,
+           Cin, Cout, k, k, pad, dp(nhwc(ref_act, prec)), dp(scale.to(DEV)), Cin, Cout, st())
     torch.cuda.synchronize()
     got = from_nhwc(out)
     e = relerr(got, ref)
@@ -152,7 +169,7 @@ def test_conv_wgrad(prec, case):
     ref = dw.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin)
     out = torch.zeros((Cout, k * k * Cin), device=DEV, dtype=torch.float32)
     L = lib()
-    L.call("szn_conv_wgrad", dcode(prec), nhwc(x, prec).data_ptr(), nhwc(dy, prec).data_ptr(), out.data_ptr(), B, H, W,
+    L.call("szn_conv_wgrad", dcode(prec), dp(nhwc(x, prec)), dp(nhwc(dy, prec)), dp(out), B, H, W,
            Cin, Cout, k, k, pad, Cout, st())
     torch.cuda.synchronize()
     e = relerr(out.cpu(), ref)
@@ -171,15 +188,15 @@ def test_conv1_1(prec):
     Ho, Wo = y.shape[2:]
     out = torch.empty((B, Ho, Wo, 64), device=DEV, dtype=tdtype(prec))
     L = lib()
-    L.call("szn_conv1_1_fwd", dcode(prec), x.to(DEV).data_ptr(), w.detach().to(DEV).data_ptr(), b.to(DEV).data_ptr(),
-           out.data_ptr(), B, H, W, 100, st())
+    L.call("szn_conv1_1_fwd", dcode(prec), dp(x.to(DEV)), dp(w.detach().to(DEV)), dp(b.to(DEV)),
+           dp(out), B, H, W, 100, st())
     torch.cuda.synchronize()
     assert relerr(from_nhwc(out), y.detach()) < (1e-3 if prec == "tf32" else 1e-2)
     dy = round_to(torch.randn(y.shape, generator=g), prec)
     pre = F.conv2d(x, w, padding=100)
     (dw,) = torch.autograd.grad(pre, w, dy)
     gw = torch.zeros((64, 3, 3, 3), device=DEV)
-    L.call("szn_conv1_1_wgrad", dcode(prec), x.to(DEV).data_ptr(), nhwc(dy, prec).data_ptr(), gw.data_ptr(), B, H, W, 100,
+    L.call("szn_conv1_1_wgrad", dcode(prec), dp(x.to(DEV)), dp(nhwc(dy, prec)), dp(gw), B, H, W, 100,
            st())
     torch.cuda.synchronize()
     assert relerr(gw.cpu(), dw) < 1e-4
@@ -199,14 +216,14 @@ def test_pool(prec, hw):
     out = torch.empty((B, p.shape[2], p.shape[3], C), device=DEV, dtype=tdtype(prec))
     L = lib()
     yd = nhwc(y.detach(), prec)
-    L.call("szn_pool_fwd", dcode(prec), yd.data_ptr(), out.data_ptr(), B, H, W, C, st())
+    L.call("szn_pool_fwd", dcode(prec), dp(yd), dp(out), B, H, W, C, st())
     torch.cuda.synchronize()
     assert torch.equal(from_nhwc(out), p.detach())
-    dp = round_to(torch.randn(p.shape, generator=g), prec)
-    (dy,) = torch.autograd.grad(p, y, dp)
+    dpool = round_to(torch.randn(p.shape, generator=g), prec)
+    (dy,) = torch.autograd.grad(p, y, dpool)
     ref = dy * (y.detach() > 0)
     dyo = torch.empty((B, H, W, C), device=DEV, dtype=tdtype(prec))
-    L.call("szn_pool_bwd", dcode(prec), yd.data_ptr(), nhwc(dp, prec).data_ptr(), dyo.data_ptr(), B, H, W, C, 1, st())
+    L.call("szn_pool_bwd", dcode(prec), dp(yd), dp(nhwc(dpool, prec)), dp(dyo), B, H, W, C, 1, st())
     torch.cuda.synchronize()
     assert torch.equal(from_nhwc(dyo), ref)
 
@@ -218,18 +235,18 @@ def test_bias_grad_pack_unpack(prec):
     dy = round_to(torch.randn(rows, ld, generator=g), prec)
     db = torch.zeros(C, device=DEV)
     L = lib()
-    L.call("szn_bias_grad", dcode(prec), dy.to(DEV).to(tdtype(prec)).data_ptr(), db.data_ptr(), rows, C, ld, st())
+    L.call("szn_bias_grad", dcode(prec), dp(dy.to(DEV).to(tdtype(prec))), dp(db), rows, C, ld, st())
     torch.cuda.synchronize()
     assert relerr(db.cpu(), dy.sum(0)) < 1e-5
     w = torch.randn(5, 64, 3, 3, generator=g)
     out = torch.empty((8, 9, 64), device=DEV, dtype=tdtype(prec))
-    L.call("szn_pack_weight", dcode(prec), w.to(DEV).data_ptr(), out.data_ptr(), 5, 64, 3, 3, 8, st())
+    L.call("szn_pack_weight", dcode(prec), dp(w.to(DEV)), dp(out), 5, 64, 3, 3, 8, st())
     torch.cuda.synchronize()
     ref = round_to(w, prec).permute(0, 2, 3, 1).reshape(5, 9, 64)
     assert torch.equal(out.float().cpu()[:5], ref) and (out.float().cpu()[5:] == 0).all()
     dw = torch.randn(5, 9, 64, generator=g)
     gg = torch.empty((5, 64, 3, 3), device=DEV)
-    L.call("szn_unpack_wgrad", dw.to(DEV).data_ptr(), gg.data_ptr(), 5, 64, 3, 3, st())
+    L.call("szn_unpack_wgrad", dp(dw.to(DEV)), dp(gg), 5, 64, 3, 3, st())
     torch.cuda.synchronize()
     assert torch.equal(gg.cpu(), dw.reshape(5, 3, 3, 64).permute(0, 3, 1, 2))
 
@@ -255,13 +272,13 @@ def test_upsample_and_small_deconv(HW):
     full = F.conv_transpose2d(sref, wdiag, stride=32)[:, :, 19:19 + H, 19:19 + W]
     L = lib()
     out = torch.empty((B, D, H, W), device=DEV)
-    L.call("szn_upsample32_crop_fwd", s.to(DEV).data_ptr(), out.data_ptr(), B, D, H, W, hs, ws, ld, 0, st())
+    L.call("szn_upsample32_crop_fwd", dp(s.to(DEV)), dp(out), B, D, H, W, hs, ws, ld, 0, st())
     torch.cuda.synchronize()
     assert relerr(out.cpu(), full.detach()) < 1e-5
     gout = torch.randn(B, D, H, W, generator=g)
     (ds_ref,) = torch.autograd.grad(full, sref, gout)
     ds = torch.zeros((B, hs, ws, ld), device=DEV)
-    L.call("szn_upsample32_crop_bwd", 0, gout.to(DEV).data_ptr(), ds.data_ptr(), B, D, H, W, hs, ws, ld, 0, st())
+    L.call("szn_upsample32_crop_bwd", 0, dp(gout.to(DEV)), dp(ds), B, D, H, W, hs, ws, ld, 0, st())
     torch.cuda.synchronize()
     got = ds.cpu().permute(0, 3, 1, 2)[:, :D]
     assert relerr(got, round_to(ds_ref, "tf32")) < 1e-3
@@ -270,17 +287,17 @@ def test_upsample_and_small_deconv(HW):
     s2 = s_nchw[:, D:D + 2].clone().requires_grad_(True)
     y2 = F.conv_transpose2d(s2, wd, stride=32)[:, :, 19:19 + H, 19:19 + W]
     o2 = torch.empty((B, 2, H, W), device=DEV)
-    L.call("szn_deconv_small_fwd", s.to(DEV).data_ptr(), wd.detach().to(DEV).data_ptr(), o2.data_ptr(), B, 2, 2, H, W,
+    L.call("szn_deconv_small_fwd", dp(s.to(DEV)), dp(wd.detach().to(DEV)), dp(o2), B, 2, 2, H, W,
            hs, ws, ld, D, st())
     torch.cuda.synchronize()
     assert relerr(o2.cpu(), y2.detach()) < 1e-5
     g2 = torch.randn(B, 2, H, W, generator=g)
     ds2_ref, dwd_ref = torch.autograd.grad(y2, (s2, wd), g2)
     ds2 = torch.zeros((B, hs, ws, ld), device=DEV)
-    L.call("szn_deconv_small_dgrad", 0, g2.to(DEV).data_ptr(), wd.detach().to(DEV).data_ptr(), ds2.data_ptr(), B, 2, 2, H,
+    L.call("szn_deconv_small_dgrad", 0, dp(g2.to(DEV)), dp(wd.detach().to(DEV)), dp(ds2), B, 2, 2, H,
            W, hs, ws, ld, D, st())
     dwd = torch.empty((2, 2, 64, 64), device=DEV)
-    L.call("szn_deconv_small_wgrad", s.to(DEV).data_ptr(), g2.to(DEV).data_ptr(), dwd.data_ptr(), B, 2, 2, H, W, hs, ws,
+    L.call("szn_deconv_small_wgrad", dp(s.to(DEV)), dp(g2.to(DEV)), dp(dwd), B, 2, 2, H, W, hs, ws,
            ld, D, st())
     torch.cuda.synchronize()
     assert relerr(ds2.cpu().permute(0, 3, 1, 2)[:, D:D + 2], round_to(ds2_ref, "tf32")) < 1e-3

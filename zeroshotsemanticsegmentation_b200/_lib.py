@@ -66,9 +66,21 @@ def load():
     return lib
 
 
+_profiler = None
+
+
+def set_profiler(fn):
+    """``fn(name, args) -> done()`` brackets every C-ABI call (bench.py's per-kernel CUDA-event timing); None disables."""
+    global _profiler
+    _profiler = fn
+
+
 def call(name, *args):
     lib = load()
+    done = _profiler(name, args) if _profiler is not None else None
     rc = getattr(lib, name)(*args)
+    if done is not None:
+        done()
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.szn_last_error().decode()))
 

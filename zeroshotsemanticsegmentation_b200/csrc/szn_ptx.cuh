@@ -141,14 +141,19 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor, SWIZZLE_128B, Blackwell version bits.
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4
 //   [46,48) version = 1         [49,52) base offset = 0            [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   layout type 1 = SWIZZLE_128B_BASE32B (32-byte swizzle atoms, 4-row groups): the ONLY layout tcgen05 accepts for
+//   MN-major 32-bit (tf32) operands; it is what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= 1ull << 46;
-  d |= 2ull << 61;
+  d |= (uint64_t)layout << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return umma_desc(saddr, lbo_bytes, sbo_bytes, 2);
 }
 
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, dense, no negate:

@@ -188,10 +188,13 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         // K-major: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzled row.
-        // MN-major: 128 B-wide groups KC*128 B apart (LBO), 8-row K groups 1024 B apart (SBO), K advances UK rows.
-        const uint64_t adesc = A_MN ? umma_desc_sw128(a_addr + k * UK * 128, KC * 128, 1024)
+        // MN-major: 128 B-wide groups KC*128 B apart (LBO), K advances UK rows of 128 B; the K rows come in groups
+        // SBO apart: 8 rows / 1024 B for 16-bit operands (SWIZZLE_128B), 4 rows / 512 B for tf32
+        // (SWIZZLE_128B_BASE32B, the only MN-major layout tcgen05 takes for 32-bit operands).
+        constexpr uint32_t MN_LAYOUT = TF32 ? 1u : 2u, MN_SBO = TF32 ? 512u : 1024u;
+        const uint64_t adesc = A_MN ? umma_desc(a_addr + k * UK * 128, KC * 128, MN_SBO, MN_LAYOUT)
                                     : umma_desc_sw128(a_addr + k * 32, 16, 1024);
-        const uint64_t bdesc = B_MN ? umma_desc_sw128(b_addr + k * UK * 128, KC * 128, 1024)
+        const uint64_t bdesc = B_MN ? umma_desc(b_addr + k * UK * 128, KC * 128, MN_SBO, MN_LAYOUT)
                                     : umma_desc_sw128(b_addr + k * 32, 16, 1024);
         tc_mma<TF32>(tmem, adesc, bdesc, idesc, (uint32_t)((it | k) != 0));
       }
@@ -354,7 +357,7 @@ static EncodeTiledFn get_encode() {
 
 // dims/box innermost first; strides in elements for dims 1..rank-1
 static int make_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const long long* dims,
-                     const long long* strides_elems, const int* box) {
+                     const long long* strides_elems, const int* box, bool mn_major = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(SZN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const int es = dtype == SZN_BF16 ? 2 : 4;
@@ -371,7 +374,9 @@ static int make_tmap(CUtensorMap* m, int dtype, const void* base, int rank, cons
   if (reinterpret_cast<uintptr_t>(base) % 16) return set_error(SZN_ERR_ARG, "TMA base not 16-byte aligned");
   CUresult r = enc(m, dtype == SZN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                    (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, el, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   // operands consumed MN-major in tf32 need 32-byte swizzle atoms (see umma_desc)
+                   (mn_major && dtype == SZN_F32) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[160];
     snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d) rank %d dims %lld %lld box %d %d", (int)r, rank,
@@ -516,7 +521,7 @@ extern "C" int szn_conv_dgrad(int dtype, const void* dy, const void* wt, void* d
     if (int e = make_tmap(&ta, dtype, dy, 4, d, s, bx)) return e;
     long long d3[3] = {Cin, (long long)R * S, Cout}, s3[3] = {1, Cin, (long long)R * S * Cin};
     int bx3[3] = {KC, 1, KC};
-    if (int e = make_tmap(&tb, dtype, wt, 3, d3, s3, bx3)) return e;
+    if (int e = make_tmap(&tb, dtype, wt, 3, d3, s3, bx3, true)) return e;
   }
   const long long grid = (long long)p.tiles_x * p.tiles_y * Bq * p.n_tiles;
   return dtype == SZN_BF16 ? launch<__nv_bfloat16, 1>(ta, tb, p, grid, (cudaStream_t)stream)
@@ -553,9 +558,9 @@ extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* d
   {
     long long d[4] = {Cout, Wo, Ho, Bq}, s[4] = {1, ld_dy, (long long)Wo * ld_dy, (long long)Ho * Wo * ld_dy};
     int bx[4] = {KC, p.TW, p.TH, 1};
-    if (int e = make_tmap(&ta, dtype, dy, 4, d, s, bx)) return e;
+    if (int e = make_tmap(&ta, dtype, dy, 4, d, s, bx, true)) return e;
     long long d2[4] = {Cin, Wq, Hq, Bq}, s2[4] = {1, Cin, (long long)Wq * Cin, (long long)Hq * Wq * Cin};
-    if (int e = make_tmap(&tb, dtype, x, 4, d2, s2, bx)) return e;
+    if (int e = make_tmap(&tb, dtype, x, 4, d2, s2, bx, true)) return e;
   }
   const long long grid = tiles * p.splits;
   return dtype == SZN_BF16 ? launch<__nv_bfloat16, 2>(ta, tb, p, grid, (cudaStream_t)stream)

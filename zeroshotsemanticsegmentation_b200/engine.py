@@ -77,6 +77,26 @@ def is_diag_bilinear(w):
     return int(torch.count_nonzero(w)) == int(torch.count_nonzero(diag))
 
 
+def _finish(module, grads):
+    if module._grad_flush is not None:
+        module._grad_flush()
+    return (None, None) + tuple(grads[n] for n in PARAM_ORDER)
+
+
+class _GradDict(dict):
+    """name -> gradient; tells ``on_ready(name, tensor)`` (the data-parallel reducer) the moment a gradient is final,
+    so its all-reduce overlaps the rest of the backward pass."""
+
+    def __init__(self, on_ready):
+        super().__init__()
+        self.on_ready = on_ready
+
+    def __setitem__(self, k, v):
+        dict.__setitem__(self, k, v)
+        if v is not None and self.on_ready is not None:
+            self.on_ready(k, v)
+
+
 class FCN32sFunction(torch.autograd.Function):
     """(x, *params) -> (f, s); both heads are always evaluated (models.py:145-151)."""
 
@@ -185,7 +205,9 @@ class FCN32sFunction(torch.autograd.Function):
         dev = sv["x"].device
         pw = module._packed
         need = {n: g for n, g in zip(PARAM_ORDER, ctx.needs_input_grad[2:])}
-        grads = {n: None for n in PARAM_ORDER}
+        grads = _GradDict(module._grad_ready)
+        for n in PARAM_ORDER:
+            dict.__setitem__(grads, n, None)
 
         def packed(name):
             return pw.cache[(name, dt)][1]
@@ -236,7 +258,7 @@ class FCN32sFunction(torch.autograd.Function):
             if need["seenmask_score.bias"]:
                 grads["seenmask_score.bias"] = dbh[D:D + 2]
         if first_needed is None:
-            return (None, None) + tuple(grads[n] for n in PARAM_ORDER)
+            return _finish(module, grads)
 
         drop = sv["drop"]
         d7 = torch.empty((B, hs, ws, 4096), device=dev, dtype=tdtype)
@@ -273,7 +295,7 @@ class FCN32sFunction(torch.autograd.Function):
                            drop[0] if drop is not None else None)
         del d7
         if d6 is None:
-            return (None, None) + tuple(grads[n] for n in PARAM_ORDER)
+            return _finish(module, grads)
         g = conv_backward("fc6", acts["pool5"], d6, h5, w5, 512, 4096, 7, 0, first_needed <= n_convs - 3, None)
         del d6
         # walk the trunk backwards
@@ -309,4 +331,4 @@ class FCN32sFunction(torch.autograd.Function):
                     g = conv_backward(name, acts[prev], g, xh, xw, cin, cout, k, pad, first_needed < ci,
                                       None if prev_is_pool else acts[prev])
             i -= 1
-        return (None, None) + tuple(grads[n] for n in PARAM_ORDER)
+        return _finish(module, grads)

@@ -70,6 +70,8 @@ class FCN32s(nn.Module):
         self.seenmask_upscore = nn.ConvTranspose2d(2, 2, 64, stride=32, bias=False)
         self._initialize_weights()
         self._packed = engine.PackedWeights()
+        self._grad_ready = None   # data-parallel hook: fn(name, grad) called as each gradient is final (ddp.py)
+        self._grad_flush = None   # data-parallel hook: fn() called once at the end of backward
         self._forced_drop_masks = None  # tests inject Dropout2d masks here: (m6, m7), each (B,4096) in {0,1}
 
     def _initialize_weights(self):

@@ -134,6 +134,11 @@ def _labels_device(score, embed_arr):
     return out
 
 
+def infer_lbl_device(score, embed_arr):
+    """``infer_lbl`` that leaves the (n,h,w) int64 labels on the device (no D2H, no numpy)."""
+    return _labels_device(score, embed_arr)
+
+
 def infer_lbl(score, embed_arr, cuda=True):
     """Nearest class embedding by cosine similarity, zero rows score 0 (``utils.py:159-185``).
     Returns an ``np.ndarray`` (n,h,w) int64 like the reference."""
