@@ -72,45 +72,89 @@ def init_params(n_class: int = 21, seed: int = 1337) -> dict:
     return p
 
 
-def trunk_forward(x, p, drop_masks=None, collect=None):
+def round_storage(t, storage):
+    """Round an fp32 tensor to what the CUDA path stores: 'tf32' = cvt.rna.tf32.f32 (10-bit mantissa, nearest,
+    ties away from zero), 'bf16' = round-to-nearest-even bfloat16; None = unchanged."""
+    if storage is None:
+        return t
+    if storage == "bf16":
+        return t.bfloat16().float()
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class _RoundSTE(torch.autograd.Function):
+    """y = round(x) in the forward pass (if ``fwd``), dx = round(dy) in the backward pass: the places where the
+    CUDA path writes an activation / a data gradient to HBM in its storage type."""
+
+    @staticmethod
+    def forward(ctx, x, storage, fwd):
+        ctx.storage = storage
+        return round_storage(x, storage) if fwd else x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return round_storage(g, ctx.storage), None, None
+
+
+def _st(t, storage, fwd=True):
+    return t if storage is None else _RoundSTE.apply(t, storage, fwd)
+
+
+def _w(p, name, storage):
+    """conv weight as the tensor-core kernels read it (rounded to the storage type; gradient passes through)."""
+    w = p[name + ".weight"]
+    return w if storage is None else w + (round_storage(w.detach(), storage) - w.detach())
+
+
+def trunk_forward(x, p, drop_masks=None, collect=None, storage=None):
     """conv1_1 .. drop7 of FCN32s.forward (models.py:115-143).  ``drop_masks`` = (m6, m7) of shape
     (B,4096) with values in {0,1}; when given they are applied as Dropout2d(p=.5) would (x * m * 2),
-    otherwise dropout is the identity (eval mode)."""
+    otherwise dropout is the identity (eval mode).
+
+    ``storage`` ('tf32' | 'bf16' | None) makes this a *storage-precision emulation* of the CUDA path: the same
+    fp32 arithmetic, but every tensor the kernels keep in HBM in a narrower type (packed weights, activations, data
+    gradients) is rounded at the same point.  With it, ReLU / max-pool decisions agree with the GPU, so gradients can
+    be compared tightly; ``storage=None`` is the reference (fp32) semantics."""
     h = x
     for row in TRUNK:
         if len(row) == 1:
             h = F.max_pool2d(h, 2, stride=2, ceil_mode=True)
         else:
             name, _, _, _, pad = row
-            h = F.relu(F.conv2d(h, p[name + ".weight"], p[name + ".bias"], padding=pad))
+            w = p[name + ".weight"] if name == "conv1_1" else _w(p, name, storage)  # conv1_1 runs in fp32 FMA
+            h = _st(F.relu(F.conv2d(h, w, p[name + ".bias"], padding=pad)), storage)
         if collect is not None:
             collect[row[0]] = h
-    h = F.relu(F.conv2d(h, p["fc6.weight"], p["fc6.bias"]))
+    h = F.relu(F.conv2d(h, _w(p, "fc6", storage), p["fc6.bias"]))
     if drop_masks is not None:
         h = h * (drop_masks[0][:, :, None, None] * 2.0)
+    h = _st(h, storage)
     if collect is not None:
         collect["fc6"] = h
-    h = F.relu(F.conv2d(h, p["fc7.weight"], p["fc7.bias"]))
+    h = F.relu(F.conv2d(h, _w(p, "fc7", storage), p["fc7.bias"]))
     if drop_masks is not None:
         h = h * (drop_masks[1][:, :, None, None] * 2.0)
+    h = _st(h, storage)
     if collect is not None:
         collect["fc7"] = h
     return h
 
 
-def head_forward(h, p, score_name, up_name, H, W):
+def head_forward(h, p, score_name, up_name, H, W, storage=None):
     """score conv -> x32 transposed conv -> crop (models.py:145-151)."""
-    s = F.conv2d(h, p[score_name + ".weight"], p[score_name + ".bias"])
+    s = F.conv2d(h, _w(p, score_name, storage), p[score_name + ".bias"])
+    s = _st(s, storage, fwd=False)  # the 17x17 score map stays fp32; its gradient is stored in the narrow type
     s = F.conv_transpose2d(s, p[up_name + ".weight"], stride=UP_S)
     return s[:, :, CROP:CROP + H, CROP:CROP + W].contiguous()
 
 
-def forward(x, p, mode="fcn", drop_masks=None, collect=None):
+def forward(x, p, mode="fcn", drop_masks=None, collect=None, storage=None):
     """FCN32s.forward (models.py:114-160): both heads always evaluated, selection by ``mode``."""
     H, W = x.shape[2], x.shape[3]
-    h = trunk_forward(x, p, drop_masks, collect)
-    f = head_forward(h, p, "score_fr", "upscore", H, W)
-    s = head_forward(h, p, "seenmask_score", "seenmask_upscore", H, W)
+    h = trunk_forward(x, p, drop_masks, collect, storage)
+    f = head_forward(h, p, "score_fr", "upscore", H, W, storage)
+    s = head_forward(h, p, "seenmask_score", "seenmask_upscore", H, W, storage)
     if mode == "fcn":
         return f
     if mode == "seenmask":

@@ -15,6 +15,20 @@ def rel(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
 
 
+def cos(a, b):
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    return float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-300))
+
+
+def emulated_grads(params, x, loss_fn, storage, drop_masks=None, mode="fcn"):
+    """Gradients of the storage-precision emulation of the CUDA path (oracle ``storage=``): fp32 arithmetic with the
+    kernels' HBM rounding points, so ReLU / max-pool decisions match the GPU and gradients compare tightly."""
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    out = O.forward(x, pr, mode, drop_masks=drop_masks, storage=storage)
+    loss_fn(out).backward()
+    return out, {k: v.grad for k, v in pr.items()}
+
+
 def build(n_class, seed, precision="tf32"):
     import zeroshotsemanticsegmentation_b200 as szn
     m = szn.FCN32s(n_class, precision=precision)
@@ -37,14 +51,28 @@ def test_forward_backward_ce21_golden(golden):
     loss = U.cross_entropy2d(score, t)
     assert abs(loss.item() - float(g["loss"])) < 1e-3 * float(g["loss"])
     loss.backward()
-    for name, tol in (("score_fr.weight", 1e-2), ("score_fr.bias", 1e-2), ("conv1_1.weight", 1e-2),
-                      ("conv1_1.bias", 1e-2), ("fc7.bias", 1e-2)):
-        got = dict(m.named_parameters())[name].grad.cpu().numpy()
-        e = rel(got, g[name.replace(".", "__") + "__grad"])
-        print(name, "grad rel err", e)
+    # (a) against the reference's fp32 gradients: the heads are tight; deep layers differ through the ReLU / max-pool
+    #     decisions that flip when activations carry TF32 (2^-11) rounding, so they are held to direction + a loose norm
+    named = dict(m.named_parameters())
+    for name, tol in (("score_fr.weight", 1e-2), ("score_fr.bias", 1e-2)):
+        e = rel(named[name].grad.cpu().numpy(), g[name.replace(".", "__") + "__grad"])
+        print(name, "grad rel err vs reference", e)
         assert e < tol
-    assert rel(m.conv3_2.weight.grad[::16, ::16].cpu().numpy(), g["conv3_2__weight__grad_sub"]) < 1e-2
-    assert rel(m.fc6.weight.grad[::256, ::64].cpu().numpy(), g["fc6__weight__grad_sub"]) < 1e-2
+    for name in ("conv1_1.weight", "conv1_1.bias", "fc7.bias"):
+        c = cos(named[name].grad.cpu().numpy(), g[name.replace(".", "__") + "__grad"])
+        print(name, "grad cosine vs reference", c)
+        assert c > 0.97
+    assert cos(m.conv3_2.weight.grad[::16, ::16].cpu().numpy(), g["conv3_2__weight__grad_sub"]) > 0.98
+    assert cos(m.fc6.weight.grad[::256, ::64].cpu().numpy(), g["fc6__weight__grad_sub"]) > 0.99
+    # (b) against the storage-precision emulation of the same fp32 oracle: every gradient within 2e-3
+    _, eg = emulated_grads(O.init_params(21, int(g["seed"])), torch.from_numpy(g["x"]),
+                           lambda sc: O.cross_entropy2d(sc, torch.from_numpy(g["target"]).long()), "tf32")
+    for name, p_ in named.items():
+        if "upscore" in name:
+            continue
+        e = rel(p_.grad.cpu().numpy(), eg[name].numpy())
+        print(name, "grad rel err vs tf32-storage oracle", e)
+        assert e < 2e-3, name
     agree = (score.detach().max(1)[1].cpu().numpy() == g["lbl"]).mean()
     print("argmax agreement", agree)
     assert agree > 0.995
@@ -79,8 +107,10 @@ def test_embedding_heads_cos_golden(golden):
     assert abs(loss.item() - want) < 1e-4
     loss.backward()
     assert rel(m.score_fr.weight.grad.cpu().numpy(), g["score_fr__weight__grad"]) < 1e-2
-    assert rel(m.conv1_1.weight.grad.cpu().numpy(), g["conv1_1__weight__grad"]) < 2e-2
-    assert rel(m.conv5_3.weight.grad[::32, ::32].cpu().numpy(), g["conv5_3__weight__grad_sub"]) < 1e-2
+    c1 = cos(m.conv1_1.weight.grad.cpu().numpy(), g["conv1_1__weight__grad"])
+    c5 = cos(m.conv5_3.weight.grad[::32, ::32].cpu().numpy(), g["conv5_3__weight__grad_sub"])
+    print("grad cosine vs reference: conv1_1.weight", c1, "conv5_3.weight", c5)
+    assert c1 > 0.97 and c5 > 0.99
     lbl = U.infer_lbl(f.detach(), tab.to(DEV))
     print("label agreement vs reference", (lbl == g["lbl"]).mean())
     assert (lbl == g["lbl"]).mean() > 0.99
@@ -135,14 +165,26 @@ def test_train_mode_dropout_masks_and_bf16(precision):
     f = m(x.to(DEV))
     loss = U.mse_loss(f, lab.to(DEV), table=table.to(DEV))
     loss.backward()
-    tol_f, tol_g = (1e-3, 1e-2) if precision == "tf32" else (2e-2, 8e-2)
+    tol_f = 1e-3 if precision == "tf32" else 2e-2
     e = rel(f.detach().cpu().numpy(), f_ref.detach().numpy())
     print(precision, "forward rel err", e)
     assert e < tol_f
-    for name in ("fc6.weight", "fc7.weight", "conv4_2.weight", "conv2_1.bias", "conv1_2.weight"):
-        ge = rel(dict(m.named_parameters())[name].grad.cpu().numpy(), pr[name].grad.numpy())
-        print(precision, name, "grad rel err", ge)
-        assert ge < tol_g
+    # gradients: tight against the storage-precision emulation (same rounding points => same ReLU/pool decisions),
+    # direction-only against the plain fp32 oracle
+    f_em, eg = emulated_grads(params, x, lambda sc: O.mse_loss(sc, lab, O.target_embed_from_labels(lab, table)),
+                              precision, drop_masks=masks)
+    e = rel(f.detach().cpu().numpy(), f_em.detach().numpy())
+    print(precision, "forward rel err vs storage-precision oracle", e)
+    assert e < (1e-4 if precision == "tf32" else 2e-3)
+    named = dict(m.named_parameters())
+    for name, p_ in named.items():
+        if "upscore" in name or name.startswith("seenmask"):
+            continue
+        ge = rel(p_.grad.cpu().numpy(), eg[name].numpy())
+        c = cos(p_.grad.cpu().numpy(), pr[name].grad.numpy())
+        print(precision, name, "grad rel err vs storage-precision oracle %.3e  cosine vs fp32 oracle %.5f" % (ge, c))
+        assert ge < (2e-3 if precision == "tf32" else 2e-2), name
+        assert c > (0.97 if precision == "tf32" else 0.90), name
     # random masks: about half of the channels dropped, scaled by 2
     m._forced_drop_masks = None
     f2 = m(x.to(DEV))

@@ -20,6 +20,7 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM -> regs -> HBM).
 #include "szn_internal.h"
 #include "szn_ptx.cuh"
+#include <stdlib.h>
 
 namespace szn {
 
@@ -35,6 +36,7 @@ struct UmmaParams {
   int Cin;      // MODE 2: channels per tap inside the N index
   int block_n, n_tiles, m_tiles, stages, splits, tmem_cols;
   int zero_smem;
+  int dbg;  // timing experiments only (SZN_DBG env): bit0 skip A loads, bit1 skip B loads after the first fill
   void* out;
   long long ldo;          // row stride of out, elements
   const float* bias;      // [N] or null
@@ -142,45 +144,86 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t tx;
     if (MODE == 2) tx = (uint32_t)((128 / KC + block_n / KC) * rows_a * 128);
     else tx = (uint32_t)(rows_a * 128 + block_n * 128);
+    // All index decompositions are carried incrementally: a runtime integer division costs ~100 cycles and the
+    // producer is a single thread (round-1 profile: 19 divisions per wgrad stage made the producer the bottleneck).
+    int s = 0;
+    uint32_t ph = 0;
+    int tap = 0, cc = 0, r = 0, sx = 0;           // MODE 0/1: filter tap (r, sx) and channel chunk
+    int bb = 0, py0 = 0, px0 = 0;                 // MODE 2: pixel chunk (image, tile origin)
+    int g_ci[8], g_dx[8], g_dy[8];                // MODE 2: per 128-byte column group: channel offset and tap shift
+    const int n_groups = block_n / KC;
+    if (MODE == 2) {
+      const int bq = q_begin / tiles_per_img;
+      const int t = q_begin - bq * tiles_per_img;
+      const int ty = t / p.tiles_x;
+      bb = bq, py0 = ty * p.TH, px0 = (t - ty * p.tiles_x) * p.TW;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int nn = n0 + g * KC;
+        const int tp = nn / p.Cin;
+        g_ci[g] = nn - tp * p.Cin;
+        const int rr = tp / p.S;
+        g_dy[g] = rr - p.pad, g_dx[g] = tp - rr * p.S - p.pad;
+      }
+    }
     for (int it = 0; it < n_iters; ++it) {
-      const int s = it % stages;
-      const uint32_t ph = (uint32_t)(it / stages) & 1u;
       mbar_wait(&empty[s], ph ^ 1u);
       uint8_t* a_dst = smem + s * stage_bytes;
       uint8_t* b_dst = a_dst + A_BYTES;
-      mbar_expect_tx(&full[s], tx);
-      if (MODE == 0) {
-        const int tap = it / p.kchunks, cc = it - tap * p.kchunks;
-        const int r = tap / p.S, sx = tap - r * p.S;
-        tma_load_4d(a_dst, &tmA, &full[s], cc * KC, x0 + sx - p.pad, y0 + r - p.pad, b);
-        tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, n0);
-      } else if (MODE == 1) {
-        const int tap = it / p.kchunks, cc = it - tap * p.kchunks;
-        const int r = tap / p.S, sx = tap - r * p.S;
-        tma_load_4d(a_dst, &tmA, &full[s], cc * KC, x0 + p.pad - sx, y0 + p.pad - r, b);
-        for (int g = 0; g < block_n / KC; ++g)
-          tma_load_3d(b_dst + g * KC * 128, &tmB, &full[s], n0 + g * KC, tap, cc * KC);
+      if (p.dbg && it >= stages) {  // timing experiment: results are garbage
+        uint32_t t2 = 0;
+        const uint32_t a_tx = (MODE == 2) ? (uint32_t)((128 / KC) * rows_a * 128) : (uint32_t)(rows_a * 128);
+        if (!(p.dbg & 1)) t2 += a_tx;
+        if (!(p.dbg & 2)) t2 += tx - a_tx;
+        if (t2 == 0) {
+          mbar_arrive(&full[s]);
+        } else {
+          mbar_expect_tx(&full[s], t2);
+          if (MODE == 0) {
+            if (!(p.dbg & 1)) tma_load_4d(a_dst, &tmA, &full[s], cc * KC, x0 + sx - p.pad, y0 + r - p.pad, b);
+            if (!(p.dbg & 2)) tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, n0);
+          }
+        }
       } else {
-        const int q = q_begin + it;
-        const int bb = q / tiles_per_img;
-        const int t = q - bb * tiles_per_img;
-        const int py0 = (t / p.tiles_x) * p.TH, px0 = (t % p.tiles_x) * p.TW;
-        for (int g = 0; g < 128 / KC; ++g)
-          tma_load_4d(a_dst + g * KC * 128, &tmA, &full[s], m0 + g * KC, px0, py0, bb);
-        for (int g = 0; g < block_n / KC; ++g) {
-          const int nn = n0 + g * KC;
-          const int tap = nn / p.Cin, ci0 = nn - tap * p.Cin;
-          const int r = tap / p.S, sx = tap - r * p.S;
-          tma_load_4d(b_dst + g * KC * 128, &tmB, &full[s], ci0, px0 + sx - p.pad, py0 + r - p.pad, bb);
+        mbar_expect_tx(&full[s], tx);
+        if (MODE == 0) {
+          tma_load_4d(a_dst, &tmA, &full[s], cc * KC, x0 + sx - p.pad, y0 + r - p.pad, b);
+          tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, n0);
+        } else if (MODE == 1) {
+          tma_load_4d(a_dst, &tmA, &full[s], cc * KC, x0 + p.pad - sx, y0 + p.pad - r, b);
+          for (int g = 0; g < n_groups; ++g)
+            tma_load_3d(b_dst + g * KC * 128, &tmB, &full[s], n0 + g * KC, tap, cc * KC);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 128 / KC; ++g)
+            tma_load_4d(a_dst + g * KC * 128, &tmA, &full[s], m0 + g * KC, px0, py0, bb);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (g < n_groups)
+              tma_load_4d(b_dst + g * KC * 128, &tmB, &full[s], g_ci[g], px0 + g_dx[g], py0 + g_dy[g], bb);
+        }
+      }
+      // advance the carried indices
+      if (++s == stages) s = 0, ph ^= 1u;
+      if (MODE == 2) {
+        px0 += p.TW;
+        if (px0 >= p.tiles_x * p.TW) {
+          px0 = 0, py0 += p.TH;
+          if (py0 >= p.tiles_y * p.TH) py0 = 0, ++bb;
+        }
+      } else {
+        if (++cc == p.kchunks) {
+          cc = 0, ++tap;
+          if (++sx == p.S) sx = 0, ++r;
         }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = umma_idesc(TF32 ? 2 : 1, A_MN ? 1 : 0, B_MN ? 1 : 0, 128, block_n);
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < n_iters; ++it) {
-      const int s = it % stages;
-      const uint32_t ph = (uint32_t)(it / stages) & 1u;
       mbar_wait(&full[s], ph);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -199,6 +242,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_mma<TF32>(tmem, adesc, bdesc, idesc, (uint32_t)((it | k) != 0));
       }
       tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+      if (++s == stages) s = 0, ph ^= 1u;
     }
     tc_commit(accf);  // accumulator complete
   } else if (warp >= 2) {
@@ -423,6 +467,11 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, UmmaParams& p, lon
   if (stages < 3) stages = (220 * 1024) / stage_bytes > 6 ? 6 : (220 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("SZN_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = MODE == 0 ? dbg : 0;
+  }
   p.tmem_cols = tmem_cols_for(p.block_n);
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
   static bool attr_set = false;
@@ -437,6 +486,16 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, UmmaParams& p, lon
   if (e != cudaSuccess) return set_error(SZN_ERR_CUDA, cudaGetErrorString(e));
   count_launch();
   return 0;
+}
+
+// shrink the N tile while the launch would leave SMs idle (fewer CTAs than SMs), keeping N % block_n == 0
+static int fill_sms(int block_n, int N, int gran, long long m_tiles) {
+  while (block_n > 64 && m_tiles * ((N + block_n - 1) / block_n) < 148) {
+    int nb = block_n / 2;
+    if (nb % gran || N % nb) break;
+    block_n = nb;
+  }
+  return block_n;
 }
 
 static int pick_block_n(int N, int gran, int maxn) {
@@ -478,6 +537,7 @@ extern "C" int szn_conv_fwd(int dtype, const void* x, const void* wt, const floa
   p.H = Ho, p.W = Wo, p.R = R, p.S = S, p.pad = pad, p.Ck = Cin, p.kchunks = ceil_div(Cin, KC);
   p.N = Cout;
   p.block_n = pick_block_n(Cout, 32, Cout >= 256 ? 256 : 128);
+  p.block_n = fill_sms(p.block_n, Cout, 32, (long long)p.tiles_x * p.tiles_y * Bq);
   p.n_tiles = ceil_div(Cout, p.block_n);
   p.out = y, p.ldo = ldo, p.bias = bias, p.scale = scale, p.scale_ld = scale_ld, p.relu = relu, p.out_fp32 = out_fp32;
   CUtensorMap ta, tb;
@@ -512,6 +572,7 @@ extern "C" int szn_conv_dgrad(int dtype, const void* dy, const void* wt, void* d
   p.H = Hq, p.W = Wq, p.R = R, p.S = S, p.pad = pad, p.Ck = Cout, p.kchunks = ceil_div(Cout, KC);
   p.N = Cin;
   p.block_n = pick_block_n(Cin, KC, Cin >= 256 ? 256 : 128);
+  p.block_n = fill_sms(p.block_n, Cin, KC, (long long)p.tiles_x * p.tiles_y * Bq);
   p.n_tiles = ceil_div(Cin, p.block_n);
   p.out = dx, p.ldo = Cin, p.mask_ref = relu_ref, p.scale = scale, p.scale_ld = scale_ld;
   CUtensorMap ta, tb;
