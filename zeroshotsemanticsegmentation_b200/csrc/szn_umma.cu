@@ -35,10 +35,9 @@ struct UmmaParams {
   int M;        // MODE 2: valid GEMM rows (Cout)
   int Cin;      // MODE 2: channels per tap inside the N index
   int block_n, n_tiles, m_tiles, stages, splits, tmem_cols;
+  int total_tiles;  // n_tiles * m_tiles (* splits): work items of the persistent tile loop
   int zero_smem;
-  int dbg;  // timing experiments only (SZN_DBG env): bit0 skip A loads, bit1 skip B loads after the first fill
-  void* out;
-  long long ldo;          // row stride of out, elements
+  long long ldo;          // row stride of the output, elements (mask_ref shares it)
   const float* bias;      // [N] or null
   const float* scale;     // [B][scale_ld] per-(image, channel) multiplier (Dropout2d) or null
   int scale_ld;
@@ -54,13 +53,57 @@ __device__ __forceinline__ float load_as_float<float>(const float* p) { return *
 template <>
 __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
+struct TileCoord {
+  int n0, b, x0, y0, m0, q_begin, n_iters;
+};
+
+// work item -> tile coordinates; n fastest so that CTAs running side by side share the A (pixel) tile through L2.
+// One set of divisions per TILE (not per pipeline stage).
+template <int MODE>
+__device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) {
+  TileCoord t;
+  const int n_tile = tile % p.n_tiles;
+  int idx = tile / p.n_tiles;
+  t.n0 = n_tile * p.block_n;
+  t.b = t.x0 = t.y0 = t.m0 = t.q_begin = 0;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  if (MODE == 2) {
+    const int m_tile = idx % p.m_tiles, split = idx / p.m_tiles;
+    t.m0 = m_tile * 128;
+    const int total_q = tiles_per_img * p.B;
+    const int per = (total_q + p.splits - 1) / p.splits;
+    t.q_begin = split * per;
+    int q_end = t.q_begin + per;
+    if (q_end > total_q) q_end = total_q;
+    t.n_iters = q_end - t.q_begin;
+    if (t.n_iters < 0) t.n_iters = 0;
+  } else {
+    t.b = idx / tiles_per_img;
+    const int r = idx - t.b * tiles_per_img;
+    const int ty = r / p.tiles_x;
+    t.y0 = ty * p.TH;
+    t.x0 = (r - ty * p.tiles_x) * p.TW;
+    t.n_iters = p.R * p.S * p.kchunks;
+  }
+  return t;
+}
+
+// Persistent, warp-specialised implicit-GEMM kernel.  grid = min(#tiles, #SMs); every role walks the same static
+// tile sequence (tile = blockIdx.x + i * gridDim.x).  Three pipelines:
+//   smem ring   full[s]/empty[s]       TMA producer  -> MMA issuer
+//   TMEM        accf[2]/acce[2]        MMA issuer    -> epilogue (two accumulator buffers: the epilogue of tile i
+//                                                       overlaps the main loop of tile i+1)
+//   staging     cp.async.bulk groups   epilogue      -> TMA store (two 16 KB swizzled buffers; coalesced, clipped by
+//                                                       the tensor map, fp32 add-reduction for the split-K wgrad)
 template <typename T, int MODE>
 __global__ void __launch_bounds__(192, 1)
-umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaParams p) {
+umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const UmmaParams p) {
   constexpr bool TF32 = sizeof(T) == 4;
   constexpr int KC = 128 / (int)sizeof(T);  // contraction elements per stage
   constexpr int UK = KC / 4;                // UMMA K (16 bf16 / 8 tf32): 4 MMAs per stage
   constexpr int A_BYTES = 128 * 128;
+  constexpr int STAGING_BYTES = 128 * 128;
   constexpr bool A_MN = (MODE == 2);
   constexpr bool B_MN = (MODE != 0);
 
@@ -71,44 +114,14 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int block_n = p.block_n;
   const int stage_bytes = A_BYTES + block_n * 128;
   const int stages = p.stages;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint8_t* staging = smem + stages * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + 2 * STAGING_BYTES);
   uint64_t* empty = full + 8;
-  uint64_t* accf = empty + 8;
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(accf + 1);
+  uint64_t* accf = empty + 8;  // [2] accumulator buffer complete
+  uint64_t* acce = accf + 2;   // [2] accumulator buffer drained
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(acce + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // ---- tile decode (n fastest so that CTAs sharing an A tile are co-scheduled) ----
-  int idx = blockIdx.x;
-  const int n_tile = idx % p.n_tiles;
-  idx /= p.n_tiles;
-  int m_tile, split = 0;
-  if (MODE == 2) {
-    m_tile = idx % p.m_tiles;
-    split = idx / p.m_tiles;
-  } else {
-    m_tile = idx;
-  }
-  const int n0 = n_tile * block_n;
-
-  int b = 0, x0 = 0, y0 = 0, m0 = 0, n_iters, q_begin = 0;
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
-  if (MODE == 2) {
-    m0 = m_tile * 128;
-    const int total_q = tiles_per_img * p.B;
-    const int per = (total_q + p.splits - 1) / p.splits;
-    q_begin = split * per;
-    int q_end = q_begin + per;
-    if (q_end > total_q) q_end = total_q;
-    n_iters = q_end - q_begin;
-    if (n_iters <= 0) return;  // whole CTA exits together (uniform)
-  } else {
-    b = m_tile / tiles_per_img;
-    const int t = m_tile - b * tiles_per_img;
-    y0 = (t / p.tiles_x) * p.TH;
-    x0 = (t % p.tiles_x) * p.TW;
-    n_iters = p.R * p.S * p.kchunks;
-  }
 
   if (p.zero_smem) {
     uint4* z = reinterpret_cast<uint4*>(smem);
@@ -119,17 +132,21 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(accf, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&accf[i], 1);
+      mbar_init(&acce[i], 4);  // one arrival per epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tptr, (uint32_t)p.tmem_cols);
+    tmem_alloc(tptr, (uint32_t)(2 * p.tmem_cols));
     tmem_relinquish();
   }
   tc_fence_before();
@@ -138,83 +155,70 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem = *tptr;
 
   const int rows_a = p.TW * p.TH;  // rows written by one pixel box
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0 && lane == 0) {
     // =========================== TMA producer ===========================
+    // All index decompositions inside a tile are carried incrementally: a runtime integer division costs ~100
+    // cycles and the producer is a single thread.
     uint32_t tx;
     if (MODE == 2) tx = (uint32_t)((128 / KC + block_n / KC) * rows_a * 128);
     else tx = (uint32_t)(rows_a * 128 + block_n * 128);
-    // All index decompositions are carried incrementally: a runtime integer division costs ~100 cycles and the
-    // producer is a single thread (round-1 profile: 19 divisions per wgrad stage made the producer the bottleneck).
+    const int n_groups = block_n / KC;
     int s = 0;
     uint32_t ph = 0;
-    int tap = 0, cc = 0, r = 0, sx = 0;           // MODE 0/1: filter tap (r, sx) and channel chunk
-    int bb = 0, py0 = 0, px0 = 0;                 // MODE 2: pixel chunk (image, tile origin)
-    int g_ci[8], g_dx[8], g_dy[8];                // MODE 2: per 128-byte column group: channel offset and tap shift
-    const int n_groups = block_n / KC;
-    if (MODE == 2) {
-      const int bq = q_begin / tiles_per_img;
-      const int t = q_begin - bq * tiles_per_img;
-      const int ty = t / p.tiles_x;
-      bb = bq, py0 = ty * p.TH, px0 = (t - ty * p.tiles_x) * p.TW;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile<MODE>(p, tile);
+      int tap = 0, cc = 0, r = 0, sx = 0;  // MODE 0/1: filter tap (r, sx) and channel chunk
+      int bb = 0, py0 = 0, px0 = 0;        // MODE 2: pixel chunk (image, tile origin)
+      int g_ci[8], g_dx[8], g_dy[8];       // MODE 2: per 128-byte column group: channel offset and tap shift
+      if (MODE == 2) {
+        const int bq = t.q_begin / tiles_per_img;
+        const int tt = t.q_begin - bq * tiles_per_img;
+        const int ty = tt / p.tiles_x;
+        bb = bq, py0 = ty * p.TH, px0 = (tt - ty * p.tiles_x) * p.TW;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const int nn = n0 + g * KC;
-        const int tp = nn / p.Cin;
-        g_ci[g] = nn - tp * p.Cin;
-        const int rr = tp / p.S;
-        g_dy[g] = rr - p.pad, g_dx[g] = tp - rr * p.S - p.pad;
-      }
-    }
-    for (int it = 0; it < n_iters; ++it) {
-      mbar_wait(&empty[s], ph ^ 1u);
-      uint8_t* a_dst = smem + s * stage_bytes;
-      uint8_t* b_dst = a_dst + A_BYTES;
-      if (p.dbg && it >= stages) {  // timing experiment: results are garbage
-        uint32_t t2 = 0;
-        const uint32_t a_tx = (MODE == 2) ? (uint32_t)((128 / KC) * rows_a * 128) : (uint32_t)(rows_a * 128);
-        if (!(p.dbg & 1)) t2 += a_tx;
-        if (!(p.dbg & 2)) t2 += tx - a_tx;
-        if (t2 == 0) {
-          mbar_arrive(&full[s]);
-        } else {
-          mbar_expect_tx(&full[s], t2);
-          if (MODE == 0) {
-            if (!(p.dbg & 1)) tma_load_4d(a_dst, &tmA, &full[s], cc * KC, x0 + sx - p.pad, y0 + r - p.pad, b);
-            if (!(p.dbg & 2)) tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, n0);
-          }
+        for (int g = 0; g < 8; ++g) {
+          const int nn = t.n0 + g * KC;
+          const int tp = nn / p.Cin;
+          g_ci[g] = nn - tp * p.Cin;
+          const int rr = tp / p.S;
+          g_dy[g] = rr - p.pad, g_dx[g] = tp - rr * p.S - p.pad;
         }
-      } else {
+      }
+      for (int it = 0; it < t.n_iters; ++it) {
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* a_dst = smem + s * stage_bytes;
+        uint8_t* b_dst = a_dst + A_BYTES;
         mbar_expect_tx(&full[s], tx);
         if (MODE == 0) {
-          tma_load_4d(a_dst, &tmA, &full[s], cc * KC, x0 + sx - p.pad, y0 + r - p.pad, b);
-          tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, n0);
+          tma_load_4d(a_dst, &tmA, &full[s], cc * KC, t.x0 + sx - p.pad, t.y0 + r - p.pad, t.b);
+          tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0);
         } else if (MODE == 1) {
-          tma_load_4d(a_dst, &tmA, &full[s], cc * KC, x0 + p.pad - sx, y0 + p.pad - r, b);
+          tma_load_4d(a_dst, &tmA, &full[s], cc * KC, t.x0 + p.pad - sx, t.y0 + p.pad - r, t.b);
           for (int g = 0; g < n_groups; ++g)
-            tma_load_3d(b_dst + g * KC * 128, &tmB, &full[s], n0 + g * KC, tap, cc * KC);
+            tma_load_3d(b_dst + g * KC * 128, &tmB, &full[s], t.n0 + g * KC, tap, cc * KC);
         } else {
 #pragma unroll
           for (int g = 0; g < 128 / KC; ++g)
-            tma_load_4d(a_dst + g * KC * 128, &tmA, &full[s], m0 + g * KC, px0, py0, bb);
+            tma_load_4d(a_dst + g * KC * 128, &tmA, &full[s], t.m0 + g * KC, px0, py0, bb);
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             if (g < n_groups)
               tma_load_4d(b_dst + g * KC * 128, &tmB, &full[s], g_ci[g], px0 + g_dx[g], py0 + g_dy[g], bb);
         }
-      }
-      // advance the carried indices
-      if (++s == stages) s = 0, ph ^= 1u;
-      if (MODE == 2) {
-        px0 += p.TW;
-        if (px0 >= p.tiles_x * p.TW) {
-          px0 = 0, py0 += p.TH;
-          if (py0 >= p.tiles_y * p.TH) py0 = 0, ++bb;
-        }
-      } else {
-        if (++cc == p.kchunks) {
-          cc = 0, ++tap;
-          if (++sx == p.S) sx = 0, ++r;
+        if (++s == stages) s = 0, ph ^= 1u;
+        if (MODE == 2) {
+          px0 += p.TW;
+          if (px0 >= p.tiles_x * p.TW) {
+            px0 = 0, py0 += p.TH;
+            if (py0 >= p.tiles_y * p.TH) py0 = 0, ++bb;
+          }
+        } else {
+          if (++cc == p.kchunks) {
+            cc = 0, ++tap;
+            if (++sx == p.S) sx = 0, ++r;
+          }
         }
       }
     }
@@ -223,160 +227,188 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t idesc = umma_idesc(TF32 ? 2 : 1, A_MN ? 1 : 0, B_MN ? 1 : 0, 128, block_n);
     int s = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < n_iters; ++it) {
-      mbar_wait(&full[s], ph);
+    uint32_t local = 0;  // tiles this CTA has started: accumulator buffer = local & 1
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile<MODE>(p, tile);
+      if (t.n_iters == 0) continue;
+      const uint32_t buf = local & 1u, aph = (local >> 1) & 1u;
+      ++local;
+      mbar_wait(&acce[buf], aph ^ 1u);  // the epilogue has drained this accumulator buffer
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-      const uint32_t b_addr = a_addr + A_BYTES;
+      const uint32_t dacc = tmem + buf * (uint32_t)p.tmem_cols;
+      for (int it = 0; it < t.n_iters; ++it) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+        const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        // K-major: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzled row.
-        // MN-major: 128 B-wide groups KC*128 B apart (LBO), K advances UK rows of 128 B; the K rows come in groups
-        // SBO apart: 8 rows / 1024 B for 16-bit operands (SWIZZLE_128B), 4 rows / 512 B for tf32
-        // (SWIZZLE_128B_BASE32B, the only MN-major layout tcgen05 takes for 32-bit operands).
-        constexpr uint32_t MN_LAYOUT = TF32 ? 1u : 2u, MN_SBO = TF32 ? 512u : 1024u;
-        const uint64_t adesc = A_MN ? umma_desc(a_addr + k * UK * 128, KC * 128, MN_SBO, MN_LAYOUT)
-                                    : umma_desc_sw128(a_addr + k * 32, 16, 1024);
-        const uint64_t bdesc = B_MN ? umma_desc(b_addr + k * UK * 128, KC * 128, MN_SBO, MN_LAYOUT)
-                                    : umma_desc_sw128(b_addr + k * 32, 16, 1024);
-        tc_mma<TF32>(tmem, adesc, bdesc, idesc, (uint32_t)((it | k) != 0));
+        for (int k = 0; k < 4; ++k) {
+          // K-major: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzled row.
+          // MN-major: 128 B-wide groups KC*128 B apart (LBO), K advances UK rows of 128 B; the K rows come in groups
+          // SBO apart: 8 rows / 1024 B for 16-bit operands (SWIZZLE_128B), 4 rows / 512 B for tf32
+          // (SWIZZLE_128B_BASE32B, the only MN-major layout tcgen05 takes for 32-bit operands).
+          constexpr uint32_t MN_LAYOUT = TF32 ? 1u : 2u, MN_SBO = TF32 ? 512u : 1024u;
+          const uint64_t adesc = A_MN ? umma_desc(a_addr + k * UK * 128, KC * 128, MN_SBO, MN_LAYOUT)
+                                      : umma_desc_sw128(a_addr + k * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? umma_desc(b_addr + k * UK * 128, KC * 128, MN_SBO, MN_LAYOUT)
+                                      : umma_desc_sw128(b_addr + k * 32, 16, 1024);
+          tc_mma<TF32>(dacc, adesc, bdesc, idesc, (uint32_t)((it | k) != 0));
+        }
+        tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+        if (++s == stages) s = 0, ph ^= 1u;
       }
-      tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
-      if (++s == stages) s = 0, ph ^= 1u;
+      tc_commit(&accf[buf]);  // accumulator complete
     }
-    tc_commit(accf);  // accumulator complete
   } else if (warp >= 2) {
     // =========================== epilogue ===========================
-    mbar_wait(accf, 0);
-    tc_fence_after();
-    const int q4 = warp & 3;  // TMEM lane quarter this warp may read
+    constexpr int OUT_F32_ONLY = TF32 || MODE == 2;
+    const bool f32_out = OUT_F32_ONLY || p.out_fp32;
+    const int CW = f32_out ? 32 : 64;  // columns per 128-byte staging row
+    const int q4 = warp & 3;           // TMEM lane quarter this warp may read
     const int row = q4 * 32 + lane;
-    const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16);
+    const bool issuer = (threadIdx.x == 64);
+    uint32_t local = 0, chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile<MODE>(p, tile);
+      if (t.n_iters == 0) continue;
+      const uint32_t buf = local & 1u, aph = (local >> 1) & 1u;
+      ++local;
+      mbar_wait(&accf[buf], aph);
+      tc_fence_after();
+      const uint32_t tbase = tmem + buf * (uint32_t)p.tmem_cols + ((uint32_t)(q4 * 32) << 16);
 
-    bool ok;
-    size_t orow = 0;  // output row index (pixel or co)
-    int img = 0;
-    if (MODE == 2) {
-      ok = (m0 + row) < p.M;
-      orow = (size_t)(m0 + row);
-    } else {
-      const int ty = row / p.TW, tx_ = row - ty * p.TW;
-      const int y = y0 + ty, x = x0 + tx_;
-      ok = row < rows_a && y < p.H && x < p.W;
-      orow = ((size_t)b * p.H + y) * p.W + x;
-      img = (int)(orow / (size_t)p.pix_per_image);
-    }
-    for (int c0 = 0; c0 < block_n; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tbase + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (!ok) continue;
-      const int nb = n0 + c0;
-      if (nb >= p.N) continue;
-      const int nvalid = (p.N - nb) < 32 ? (p.N - nb) : 32;
-      if (MODE == 2) {
-        float* dst = reinterpret_cast<float*>(p.out) + orow * p.ldo + nb;
-        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+      bool ok = true;
+      size_t orow = 0;  // output row index (pixel) for the mask / scale lookups
+      int img = 0;
+      if (MODE != 2) {
+        const int ty = row / p.TW, tx_ = row - ty * p.TW;
+        const int y = t.y0 + ty, x = t.x0 + tx_;
+        ok = row < rows_a && y < p.H && x < p.W;
+        orow = ((size_t)t.b * p.H + y) * p.W + x;
+        img = (int)(orow / (size_t)p.pix_per_image);
+      }
+      const int n_chunks = (block_n + CW - 1) / CW;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int c0 = c * CW;
+        const int nb = t.n0 + c0;
+        const bool last = (c == n_chunks - 1) || (nb + CW >= p.N);
+        if (nb >= p.N) break;  // uniform: the whole chunk lies in the column padding
+        float f[64];
+        {
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)c0, v);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 f = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                   __uint_as_float(v[j + 3]));
-            atomicAdd(reinterpret_cast<float4*>(dst + j), f);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (!f32_out) {
+            tmem_ld32(tbase + (uint32_t)(c0 + 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[32 + j] = __uint_as_float(v[j]);
           }
-        } else {
-          for (int j = 0; j < nvalid; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
         }
-      } else {
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) f[j] += __ldg(p.bias + nb + j);
+        if (last) {  // every TMEM read of this tile is done: hand the accumulator buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acce[buf]);
         }
-        if (p.relu) {
+        const int nvalid = (p.N - nb) < CW ? (p.N - nb) : CW;
+        if (MODE != 2) {
+          if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (p.scale) {
-          const float* sc = p.scale + (size_t)img * p.scale_ld + nb;
+            for (int j = 0; j < 64; ++j)
+              if (j < CW && j < nvalid) f[j] += __ldg(p.bias + nb + j);
+          }
+          if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) f[j] *= __ldg(sc + j);
-        }
-        if (MODE == 1 && p.mask_ref) {
-          const T* ref = reinterpret_cast<const T*>(p.mask_ref) + orow * p.ldo + nb;
-          if (nvalid == 32) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(ref);
-            if (TF32) {
+            for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.scale) {
+            const float* sc = p.scale + (size_t)img * p.scale_ld + nb;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint4 u = __ldg(r4 + j);
-                if (!(__uint_as_float(u.x) > 0.f)) f[4 * j + 0] = 0.f;
-                if (!(__uint_as_float(u.y) > 0.f)) f[4 * j + 1] = 0.f;
-                if (!(__uint_as_float(u.z) > 0.f)) f[4 * j + 2] = 0.f;
-                if (!(__uint_as_float(u.w) > 0.f)) f[4 * j + 3] = 0.f;
-              }
-            } else {
+            for (int j = 0; j < 64; ++j)
+              if (j < CW && j < nvalid) f[j] *= __ldg(sc + j);
+          }
+          if (MODE == 1 && p.mask_ref && ok) {
+            const T* ref = reinterpret_cast<const T*>(p.mask_ref) + orow * p.ldo + nb;
+            if (nvalid == CW) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(ref);  // 128 contiguous bytes of this thread's row
+              if (TF32) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 u = __ldg(r4 + j);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                for (int j = 0; j < 8; ++j) {
+                  const uint4 u = __ldg(r4 + j);
+                  if (!(__uint_as_float(u.x) > 0.f)) f[4 * j + 0] = 0.f;
+                  if (!(__uint_as_float(u.y) > 0.f)) f[4 * j + 1] = 0.f;
+                  if (!(__uint_as_float(u.z) > 0.f)) f[4 * j + 2] = 0.f;
+                  if (!(__uint_as_float(u.w) > 0.f)) f[4 * j + 3] = 0.f;
+                }
+              } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                  const uint32_t lo = w[e] & 0xFFFFu, hi = w[e] >> 16;
-                  if ((lo & 0x8000u) || (lo & 0x7FFFu) == 0) f[8 * j + 2 * e] = 0.f;
-                  if ((hi & 0x8000u) || (hi & 0x7FFFu) == 0) f[8 * j + 2 * e + 1] = 0.f;
+                for (int j = 0; j < 8; ++j) {
+                  const uint4 u = __ldg(r4 + j);
+                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                    const uint32_t lo = w[e] & 0xFFFFu, hi = w[e] >> 16;
+                    if ((lo & 0x8000u) || (lo & 0x7FFFu) == 0) f[8 * j + 2 * e] = 0.f;
+                    if ((hi & 0x8000u) || (hi & 0x7FFFu) == 0) f[8 * j + 2 * e + 1] = 0.f;
+                  }
                 }
               }
+            } else {
+              for (int j = 0; j < nvalid; ++j)
+                if (!(load_as_float<T>(ref + j) > 0.f)) f[j] = 0.f;
             }
-          } else {
-            for (int j = 0; j < nvalid; ++j)
-              if (!(load_as_float<T>(ref + j) > 0.f)) f[j] = 0.f;
           }
         }
-        if (p.out_fp32 || TF32) {
-          float* dst = reinterpret_cast<float*>(p.out) + orow * p.ldo + nb;
-          if (!p.out_fp32) {
+        // ---- registers -> swizzled staging row -> TMA store ----
+        uint8_t* sbuf = staging + (chunk_ctr & 1u) * STAGING_BYTES;
+        ++chunk_ctr;
+        if (issuer) bulk_wait_read<1>();  // the store issued from this buffer two chunks ago has read it
+        named_bar_sync(1, 128);
+        uint4 q[8];
+        if (f32_out) {
+          if (TF32 && MODE != 2 && !p.out_fp32) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = to_tf32(f[j]);
           }
-          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            for (int j = 0; j < nvalid; ++j) dst[j] = f[j];
-          }
+          for (int j = 0; j < 8; ++j)
+            q[j] = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                              __float_as_uint(f[4 * j + 3]));
         } else {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nb;
-          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-              uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&h0);
-              u.y = *reinterpret_cast<uint32_t*>(&h1);
-              u.z = *reinterpret_cast<uint32_t*>(&h2);
-              u.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(dst + j) = u;
-            }
-          } else {
-            for (int j = 0; j < nvalid; ++j) dst[j] = __float2bfloat16_rn(f[j]);
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+            q[j].x = *reinterpret_cast<uint32_t*>(&h0);
+            q[j].y = *reinterpret_cast<uint32_t*>(&h1);
+            q[j].z = *reinterpret_cast<uint32_t*>(&h2);
+            q[j].w = *reinterpret_cast<uint32_t*>(&h3);
           }
+        }
+        // SWIZZLE_128B: 16-byte chunk j of row r lives at chunk (j ^ (r & 7)); conflict-free for a warp's 32 rows
+        uint4* srow = reinterpret_cast<uint4*>(sbuf + row * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) srow[j ^ (row & 7)] = q[j];
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (issuer) {
+          if (MODE == 2) tma_reduce_add_2d(&tmO, sbuf, nb, t.m0);
+          else tma_store_4d(&tmO, sbuf, nb, t.x0, t.y0, t.b);
+          bulk_commit();
         }
       }
     }
+    if (issuer) bulk_wait<0>();  // all stores have landed before the CTA (and its shared memory) goes away
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+  if (warp == 2) tmem_dealloc(tmem, (uint32_t)(2 * p.tmem_cols));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -400,6 +432,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // dims/box innermost first; strides in elements for dims 1..rank-1
+// dtype here is the ELEMENT type of the mapped tensor (SZN_F32 / SZN_BF16)
 static int make_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const long long* dims,
                      const long long* strides_elems, const int* box, bool mn_major = false) {
   EncodeTiledFn enc = get_encode();
@@ -458,22 +491,27 @@ static void pick_tile(int W, int H, int max_rows, int* TW, int* TH) {
 
 static int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
 
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <typename T, int MODE>
-static int launch(const CUtensorMap& a, const CUtensorMap& b, UmmaParams& p, long long grid, cudaStream_t st) {
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, UmmaParams& p, long long tiles,
+                  cudaStream_t st) {
   const int stage_bytes = 128 * 128 + p.block_n * 128;
-  // two CTAs per SM when they fit (one's epilogue overlaps the other's main loop)
-  int stages = (110 * 1024) / stage_bytes;
-  if (stages > 6) stages = 6;
-  if (stages < 3) stages = (220 * 1024) / stage_bytes > 6 ? 6 : (220 * 1024) / stage_bytes;
+  const int fixed = 2 * 128 * 128 /* epilogue staging */ + 1024 /* alignment */ + 256 /* barriers */;
+  int stages = (227 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("SZN_DBG"); dbg = e ? atoi(e) : 0; }
-    p.dbg = MODE == 0 ? dbg : 0;
-  }
   p.tmem_cols = tmem_cols_for(p.block_n);
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  p.total_tiles = (int)tiles;
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
@@ -481,7 +519,9 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, UmmaParams& p, lon
     if (e != cudaSuccess) return set_error(SZN_ERR_CUDA, cudaGetErrorString(e));
     attr_set = true;
   }
-  umma_conv_kernel<T, MODE><<<(unsigned)grid, 192, smem, st>>>(a, b, p);
+  // persistent: one CTA per SM walks the tile list
+  const unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
+  umma_conv_kernel<T, MODE><<<grid, 192, smem, st>>>(a, b, o, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SZN_ERR_CUDA, cudaGetErrorString(e));
   count_launch();
@@ -536,12 +576,17 @@ extern "C" int szn_conv_fwd(int dtype, const void* x, const void* wt, const floa
   p.tiles_x = ceil_div(Wo, p.TW), p.tiles_y = ceil_div(Ho, p.TH), p.B = Bq;
   p.H = Ho, p.W = Wo, p.R = R, p.S = S, p.pad = pad, p.Ck = Cin, p.kchunks = ceil_div(Cin, KC);
   p.N = Cout;
-  p.block_n = pick_block_n(Cout, 32, Cout >= 256 ? 256 : 128);
-  p.block_n = fill_sms(p.block_n, Cout, 32, (long long)p.tiles_x * p.tiles_y * Bq);
+  const int out_f32 = (dtype == SZN_F32 || out_fp32) ? 1 : 0;
+  const int ngran = out_f32 ? 32 : 64;  // the epilogue moves 128-byte output rows
+  p.block_n = pick_block_n(Cout, ngran, Cout >= 256 ? 256 : 128);
+  p.block_n = fill_sms(p.block_n, Cout, ngran, (long long)p.tiles_x * p.tiles_y * Bq);
   p.n_tiles = ceil_div(Cout, p.block_n);
-  p.out = y, p.ldo = ldo, p.bias = bias, p.scale = scale, p.scale_ld = scale_ld, p.relu = relu, p.out_fp32 = out_fp32;
-  CUtensorMap ta, tb;
+  p.ldo = ldo, p.bias = bias, p.scale = scale, p.scale_ld = scale_ld, p.relu = relu, p.out_fp32 = out_fp32;
+  CUtensorMap ta, tb, to;
   {
+    long long od[4] = {Cout, Wo, Ho, Bq}, os[4] = {1, ldo, (long long)Wo * ldo, (long long)Ho * Wo * ldo};
+    int obx[4] = {out_f32 ? 32 : 64, p.TW, p.TH, 1};
+    if (int e = make_tmap(&to, out_f32 ? SZN_F32 : SZN_BF16, y, 4, od, os, obx)) return e;
     long long d[4] = {Cin, Wq, Hq, Bq}, s[4] = {1, Cin, (long long)Wq * Cin, (long long)Hq * Wq * Cin};
     int bx[4] = {KC, p.TW, p.TH, 1};
     if (int e = make_tmap(&ta, dtype, x, 4, d, s, bx)) return e;
@@ -551,8 +596,8 @@ extern "C" int szn_conv_fwd(int dtype, const void* x, const void* wt, const floa
     if (int e = make_tmap(&tb, dtype, wt, 2, d2, s2, bx2)) return e;
   }
   const long long grid = (long long)p.tiles_x * p.tiles_y * Bq * p.n_tiles;
-  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 0>(ta, tb, p, grid, (cudaStream_t)stream)
-                           : launch<float, 0>(ta, tb, p, grid, (cudaStream_t)stream);
+  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 0>(ta, tb, to, p, grid, (cudaStream_t)stream)
+                           : launch<float, 0>(ta, tb, to, p, grid, (cudaStream_t)stream);
 }
 
 // dx[B,H,W,Cin] (the conv input's gradient) from dy[B,Ho,Wo,Cout]; optional ReLU gate by `relu_ref` (same shape as dx)
@@ -574,9 +619,12 @@ extern "C" int szn_conv_dgrad(int dtype, const void* dy, const void* wt, void* d
   p.block_n = pick_block_n(Cin, KC, Cin >= 256 ? 256 : 128);
   p.block_n = fill_sms(p.block_n, Cin, KC, (long long)p.tiles_x * p.tiles_y * Bq);
   p.n_tiles = ceil_div(Cin, p.block_n);
-  p.out = dx, p.ldo = Cin, p.mask_ref = relu_ref, p.scale = scale, p.scale_ld = scale_ld;
-  CUtensorMap ta, tb;
+  p.ldo = Cin, p.mask_ref = relu_ref, p.scale = scale, p.scale_ld = scale_ld;
+  CUtensorMap ta, tb, to;
   {
+    long long od[4] = {Cin, Wq, Hq, Bq}, os[4] = {1, Cin, (long long)Wq * Cin, (long long)Hq * Wq * Cin};
+    int obx[4] = {dtype == SZN_F32 ? 32 : 64, p.TW, p.TH, 1};
+    if (int e = make_tmap(&to, dtype, dx, 4, od, os, obx)) return e;
     long long d[4] = {Cout, Wo, Ho, Bq}, s[4] = {1, ld_dy, (long long)Wo * ld_dy, (long long)Ho * Wo * ld_dy};
     int bx[4] = {KC, p.TW, p.TH, 1};
     if (int e = make_tmap(&ta, dtype, dy, 4, d, s, bx)) return e;
@@ -585,8 +633,8 @@ extern "C" int szn_conv_dgrad(int dtype, const void* dy, const void* wt, void* d
     if (int e = make_tmap(&tb, dtype, wt, 3, d3, s3, bx3, true)) return e;
   }
   const long long grid = (long long)p.tiles_x * p.tiles_y * Bq * p.n_tiles;
-  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 1>(ta, tb, p, grid, (cudaStream_t)stream)
-                           : launch<float, 1>(ta, tb, p, grid, (cudaStream_t)stream);
+  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 1>(ta, tb, to, p, grid, (cudaStream_t)stream)
+                           : launch<float, 1>(ta, tb, to, p, grid, (cudaStream_t)stream);
 }
 
 // dw[Cout][R*S*Cin] (fp32, ACCUMULATED into: the caller zeroes it) from x[B,H,W,Cin] and dy[B,Ho,Wo,Cout]
@@ -614,9 +662,12 @@ extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* d
   if (splits < 1) splits = 1;
   p.splits = (int)splits;
   p.zero_smem = (p.TW * p.TH < KC) ? 1 : 0;
-  p.out = dw, p.ldo = p.N;
-  CUtensorMap ta, tb;
+  p.ldo = p.N;
+  CUtensorMap ta, tb, to;
   {
+    long long od[2] = {p.N, Cout}, os[2] = {1, p.N};
+    int obx[2] = {32, 128};
+    if (int e = make_tmap(&to, SZN_F32, dw, 2, od, os, obx)) return e;
     long long d[4] = {Cout, Wo, Ho, Bq}, s[4] = {1, ld_dy, (long long)Wo * ld_dy, (long long)Ho * Wo * ld_dy};
     int bx[4] = {KC, p.TW, p.TH, 1};
     if (int e = make_tmap(&ta, dtype, dy, 4, d, s, bx, true)) return e;
@@ -624,6 +675,6 @@ extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* d
     if (int e = make_tmap(&tb, dtype, x, 4, d2, s2, bx, true)) return e;
   }
   const long long grid = tiles * p.splits;
-  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 2>(ta, tb, p, grid, (cudaStream_t)stream)
-                           : launch<float, 2>(ta, tb, p, grid, (cudaStream_t)stream);
+  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 2>(ta, tb, to, p, grid, (cudaStream_t)stream)
+                           : launch<float, 2>(ta, tb, to, p, grid, (cudaStream_t)stream);
 }
