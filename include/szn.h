@@ -39,9 +39,11 @@ int szn_abi_version(void);
 int szn_conv_fwd(int dtype, const void* x, const void* wt, const float* bias, void* y, int B, int H, int W, int Cin,
                  int Cout, int R, int S, int pad, int relu, const float* scale, int scale_ld, int out_fp32,
                  long long ldo, void* stream);
-/* dx[B,H,W,Cin] = conv_transpose(dy[B,Ho,Wo,Cout] (row stride ld_dy), wt) * scale[b][ci] * (relu_ref[B,H,W,Cin] > 0) */
-int szn_conv_dgrad(int dtype, const void* dy, const void* wt, void* dx, int B, int H, int W, int Cin, int Cout, int R,
-                   int S, int pad, const void* relu_ref, const float* scale, int scale_ld, long long ld_dy,
+/* dx[B,H,W,Cin] = conv_transpose(dy[B,Ho,Wo,Cout] (row stride ld_dy), w) * scale[b][ci] * (relu_ref[B,H,W,Cin] > 0)
+ * wt_dgrad: the transposed, tap-flipped weights [Cin][R*S][Cout] written by szn_pack_weight_dgrad(mode 0); the data
+ * gradient then runs as a forward conv of dy with padding R-1-pad on the same tensor-core path. */
+int szn_conv_dgrad(int dtype, const void* dy, const void* wt_dgrad, void* dx, int B, int H, int W, int Cin, int Cout,
+                   int R, int S, int pad, const void* relu_ref, const float* scale, int scale_ld, long long ld_dy,
                    void* stream);
 /* dw[Cout][R*S*Cin] += sum_pixels dy (x) x   (fp32, split-K atomics: zero dw first) */
 int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int R,
@@ -66,6 +68,12 @@ int szn_bias_grad(int dtype, const void* dy, float* db, long long rows, int C, l
 /* parameter layout conversion between the reference's OIHW fp32 tensors (state_dict layout, models.py:43-98)
  * and the kernels' [O_pad][R*S][I] layout (rows >= O zero-filled) */
 int szn_pack_weight(int dtype, const float* w_oihw, void* out, int O, int I, int R, int S, int O_pad, void* stream);
+/* OIHW fp32 -> [Cin][R*S flipped][O_pad] (mode 0) or [R*S*Cin][O_pad] (mode 1): K-major operands of the data gradient */
+int szn_pack_weight_dgrad(int dtype, const float* w_oihw, void* out, int O, int I, int R, int S, int O_pad, int mode,
+                          void* stream);
+/* fc6 data gradient (models.py:84, 7x7 valid conv on a 23x23 map): dcol[B,Ho,Wo,R*S*C] (one GEMM against the mode-1
+ * weights) is folded back to dx[B,H,W,C] by summing the <= R*S window positions that cover each pixel */
+int szn_col2im(int dtype, const void* dcol, void* dx, int B, int H, int W, int C, int R, int S, void* stream);
 int szn_unpack_wgrad(const float* dw_ohwi, float* g_oihw, int O, int I, int R, int S, void* stream);
 int szn_cast(int dtype, const float* in, void* out, long long n, void* stream);
 

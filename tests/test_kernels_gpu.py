@@ -130,12 +130,18 @@ def test_conv_fwd_fp32_out_no_relu(prec):
     assert (got[:, Cout - 10:] == 0).all()
 
 
+def pack_dgrad(w, prec, mode=0):
+    """Transposed data-gradient weights through the library's own pack kernel (what engine.py does)."""
+    O_, I, R, S = w.shape
+    out = torch.empty((I, R * S, O_), device=DEV, dtype=tdtype(prec))
+    lib().call("szn_pack_weight_dgrad", dcode(prec), dp(w.contiguous().to(DEV)), dp(out), O_, I, R, S, O_, mode, st())
+    return out
+
+
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_dgrad(prec, case):
     B, H, W, Cin, Cout, k, pad = case
-    if Cin % 64 and prec == "bf16":
-        pytest.skip("Cin granularity")
     g = torch.Generator().manual_seed(3)
     x = torch.randn(B, Cin, H, W, generator=g).requires_grad_(True)
     w = round_to(torch.randn(Cout, Cin, k, k, generator=g) / (Cout * k * k) ** 0.5, prec)
@@ -147,13 +153,36 @@ def test_conv_dgrad(prec, case):
     ref = dx * scale[:, :, None, None] * (ref_act > 0)
     out = torch.full((B, H, W, Cin), float("nan"), device=DEV, dtype=tdtype(prec))
     L = lib()
-    L.call("szn_conv_dgrad", dcode(prec), dp(nhwc(dy, prec)), dp(ohwi(w, prec)), dp(out), B, H, W,
+    L.call("szn_conv_dgrad", dcode(prec), dp(nhwc(dy, prec)), dp(pack_dgrad(w, prec)), dp(out), B, H, W,
            Cin, Cout, k, k, pad, dp(nhwc(ref_act, prec)), dp(scale.to(DEV)), Cin, Cout, st())
     torch.cuda.synchronize()
     got = from_nhwc(out)
     e = relerr(got, ref)
     print("conv_dgrad", prec, case, "relerr", e)
     assert e < (1e-3 if prec == "tf32" else 1e-2)
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_conv_dgrad_col2im(prec):
+    """fc6-style data gradient: one GEMM against the (tap, ci)-major transposed weights + szn_col2im."""
+    B, H, W, Cin, Cout, k = 2, 11, 12, 64, 128, 7
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(B, Cin, H, W, generator=g).requires_grad_(True)
+    w = round_to(torch.randn(Cout, Cin, k, k, generator=g) / (Cout * k * k) ** 0.5, prec)
+    y = F.conv2d(x, w)
+    dy = round_to(torch.randn(y.shape, generator=g), prec)
+    (ref,) = torch.autograd.grad(y, x, dy)
+    Ho, Wo = y.shape[2:]
+    L = lib()
+    dcol = torch.full((B, Ho, Wo, k * k * Cin), float("nan"), device=DEV, dtype=tdtype(prec))
+    L.call("szn_conv_dgrad", dcode(prec), dp(nhwc(dy, prec)), dp(pack_dgrad(w, prec, 1)), dp(dcol), B, Ho, Wo,
+           k * k * Cin, Cout, 1, 1, 0, None, None, 0, Cout, st())
+    out = torch.full((B, H, W, Cin), float("nan"), device=DEV, dtype=tdtype(prec))
+    L.call("szn_col2im", dcode(prec), dp(dcol), dp(out), B, H, W, Cin, k, k, st())
+    torch.cuda.synchronize()
+    e = relerr(from_nhwc(out), ref)
+    print("conv_dgrad_col2im", prec, "relerr", e)
+    assert e < (1e-3 if prec == "tf32" else 2e-2)
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])

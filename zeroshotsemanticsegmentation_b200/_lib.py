@@ -23,6 +23,8 @@ SIGNATURES = {
     "szn_pool_bwd": [I, P, P, P, I, I, I, I, I, P],
     "szn_bias_grad": [I, P, P, LL, I, LL, P],
     "szn_pack_weight": [I, P, P, I, I, I, I, I, P],
+    "szn_pack_weight_dgrad": [I, P, P, I, I, I, I, I, I, P],
+    "szn_col2im": [I, P, P, I, I, I, I, I, I, P],
     "szn_unpack_wgrad": [P, P, I, I, I, I, P],
     "szn_cast": [I, P, P, LL, P],
     "szn_dropout_scale": [P, I, ULL, P],

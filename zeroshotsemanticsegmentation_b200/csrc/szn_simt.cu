@@ -276,6 +276,67 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     out[i] = from_float<T>(o < O ? w[((long long)o * I + ci) * RS + rs] : 0.f);
   }
 }
+// OIHW fp32 -> the transposed layouts the data-gradient GEMMs read (K = output channel, contiguous):
+//   mode 0: out[ci][(R-1-r)*S + (S-1-s)][co]   dgrad as a forward conv of dY with flipped taps
+//   mode 1: out[(r*S+s)*I + ci][co]            dgrad as one GEMM producing per-tap columns (then szn_col2im)
+// co >= O is zero-filled up to O_pad.
+template <typename T>
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, int O, int I, int R, int S,
+                                         int O_pad, int mode) {
+  const int RS = R * S;
+  const long long total = (long long)I * RS * O_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % O_pad);
+    const long long row = i / O_pad;
+    int ci, tap;
+    if (mode == 0) {
+      ci = (int)(row / RS);
+      tap = RS - 1 - (int)(row - (long long)ci * RS);  // flipped in both r and s
+    } else {
+      tap = (int)(row / I);
+      ci = (int)(row - (long long)tap * I);
+    }
+    out[i] = from_float<T>(co < O ? w[((long long)co * I + ci) * RS + tap] : 0.f);
+  }
+}
+
+// dx[b,Y,X,ci] = sum_{r,s} dcol[b, Y-r, X-s, (r*S+s)*C + ci]   (valid conv, pad 0): the scatter-free transpose of im2col
+template <typename T>
+__global__ void col2im_kernel(const T* __restrict__ dcol, T* __restrict__ dx, int B, int H, int W, int C, int R, int S) {
+  constexpr int VN = 16 / sizeof(T);
+  const int Ho = H - R + 1, Wo = W - S + 1, cv = C / VN;
+  const long long total = (long long)B * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    long long q = i / cv;
+    const int X = (int)(q % W);
+    q /= W;
+    const int Y = (int)(q % H);
+    const int b = (int)(q / H);
+    float acc[VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) acc[j] = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const int y = Y - r;
+      if (y < 0 || y >= Ho) continue;
+      for (int sx = 0; sx < S; ++sx) {
+        const int x = X - sx;
+        if (x < 0 || x >= Wo) continue;
+        const T* src = dcol + ((((long long)b * Ho + y) * Wo + x) * (R * S) + (r * S + sx)) * C;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + c);
+        const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) acc[j] += as_float<T>(e[j]);
+      }
+    }
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) oe[j] = from_float<T>(acc[j]);
+    reinterpret_cast<uint4*>(dx + (((long long)b * H + Y) * W + X) * C)[c] = o;
+  }
+}
+
 // [O_pad][R*S][I] fp32 -> OIHW fp32
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ g, int O, int I, int RS) {
   const long long total = (long long)O * RS * I;
@@ -382,6 +443,21 @@ extern "C" int szn_pack_weight(int dtype, const float* w_oihw, void* out, int O,
   const long long total = (long long)O_pad * R * S * I;
   DISPATCH_T(dtype, (pack_weight_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (T*)out, O, I, R * S, O_pad)));
   return check_launch("szn_pack_weight");
+}
+
+extern "C" int szn_pack_weight_dgrad(int dtype, const float* w_oihw, void* out, int O, int I, int R, int S, int O_pad,
+                                     int mode, void* stream) {
+  const long long total = (long long)I * R * S * O_pad;
+  DISPATCH_T(dtype, (pack_weight_dgrad_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (T*)out, O, I, R, S, O_pad, mode)));
+  return check_launch("szn_pack_weight_dgrad");
+}
+
+extern "C" int szn_col2im(int dtype, const void* dcol, void* dx, int B, int H, int W, int C, int R, int S, void* stream) {
+  const int vn = dtype == SZN_BF16 ? 8 : 4;
+  if (C % vn) return set_error(SZN_ERR_ARG, "szn_col2im: C must be a multiple of 16 bytes");
+  const long long total = (long long)B * H * W * (C / vn);
+  DISPATCH_T(dtype, (col2im_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dcol, (T*)dx, B, H, W, C, R, S)));
+  return check_launch("szn_col2im");
 }
 
 extern "C" int szn_unpack_wgrad(const float* dw_ohwi, float* g_oihw, int O, int I, int R, int S, void* stream) {

@@ -8,8 +8,8 @@
 //               (KC channels x TW x TH pixels) at the tap-shifted coordinate; out-of-image pixels are
 //               zero-filled by TMA, which implements the conv padding (pad=1, and pad=6 of the fc6 dgrad).
 //           B = weights [Cout][taps*Cin], K-major, 2-D TMA boxes.
-//   MODE 1  dgrad     D[pixel, ci] = sum_{tap, co} dY[pixel + pad - tap, co] * Wt[co, tap, ci]
-//           A = dY (K-major), B = the SAME weight buffer read MN-major (ci contiguous), 3-D TMA boxes.
+//           dgrad runs on the same path: it is the forward conv of dY with the transposed, flipped weights
+//           (szn_pack_weight_dgrad) and padding R-1-pad; its epilogue fuses the ReLU gate and the Dropout2d scale.
 //   MODE 2  wgrad     D[co, (tap, ci)] = sum_{pixel} dY[pixel, co] * X[pixel + tap - pad, ci]
 //           both operands MN-major (the reduction runs over pixels), split-K over pixel chunks,
 //           fp32 atomics into dW[Cout][taps*Cin].
@@ -37,12 +37,13 @@ struct UmmaParams {
   int block_n, n_tiles, m_tiles, stages, splits, tmem_cols;
   int total_tiles;  // n_tiles * m_tiles (* splits): work items of the persistent tile loop
   int zero_smem;
+  int dbg;  // timing experiments only (SZN_DBG / SZN_DBG_MODE env): bit0 skip A loads, bit1 skip B loads
   long long ldo;          // row stride of the output, elements (mask_ref shares it)
   const float* bias;      // [N] or null
   const float* scale;     // [B][scale_ld] per-(image, channel) multiplier (Dropout2d) or null
   int scale_ld;
   int pix_per_image;      // rows per image for the scale lookup (H*W, or the original H*W when flattened)
-  const void* mask_ref;   // MODE 1: activation whose sign gates the gradient (ReLU backward) or null
+  const void* mask_ref;   // dgrad: activation whose sign gates the gradient (ReLU backward) or null
   int relu, out_fp32;
 };
 
@@ -105,7 +106,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int A_BYTES = 128 * 128;
   constexpr int STAGING_BYTES = 128 * 128;
   constexpr bool A_MN = (MODE == 2);
-  constexpr bool B_MN = (MODE != 0);
+  constexpr bool B_MN = (MODE == 2);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -159,17 +160,17 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     // =========================== TMA producer ===========================
-    // All index decompositions inside a tile are carried incrementally: a runtime integer division costs ~100
-    // cycles and the producer is a single thread.
-    uint32_t tx;
-    if (MODE == 2) tx = (uint32_t)((128 / KC + block_n / KC) * rows_a * 128);
-    else tx = (uint32_t)(rows_a * 128 + block_n * 128);
+    // One thread; all index decompositions inside a tile are carried incrementally (a runtime integer division costs
+    // ~100 cycles; 19 of them per wgrad stage made the producer the bottleneck in the first profile).
+    constexpr int A_BOXES = (MODE == 2) ? 128 / KC : 1;
     const int n_groups = block_n / KC;
+    const uint32_t a_tx = (uint32_t)(A_BOXES * rows_a * 128);
+    const uint32_t b_tx = (MODE == 2) ? (uint32_t)(n_groups * rows_a * 128) : (uint32_t)(block_n * 128);
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<MODE>(p, tile);
-      int tap = 0, cc = 0, r = 0, sx = 0;  // MODE 0/1: filter tap (r, sx) and channel chunk
+      int tap = 0, cc = 0, r = 0, sx = 0;  // MODE 0: filter tap (r, sx) and channel chunk
       int bb = 0, py0 = 0, px0 = 0;        // MODE 2: pixel chunk (image, tile origin)
       int g_ci[8], g_dx[8], g_dy[8];       // MODE 2: per 128-byte column group: channel offset and tap shift
       if (MODE == 2) {
@@ -190,22 +191,25 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&empty[s], ph ^ 1u);
         uint8_t* a_dst = smem + s * stage_bytes;
         uint8_t* b_dst = a_dst + A_BYTES;
-        mbar_expect_tx(&full[s], tx);
+        const bool skip_a = (p.dbg & 1) && it >= stages, skip_b = (p.dbg & 2) && it >= stages;  // timing experiments
+        const uint32_t tx = (skip_a ? 0u : a_tx) + (skip_b ? 0u : b_tx);
+        if (tx) mbar_expect_tx(&full[s], tx);
+        else mbar_arrive(&full[s]);
         if (MODE == 0) {
-          tma_load_4d(a_dst, &tmA, &full[s], cc * KC, t.x0 + sx - p.pad, t.y0 + r - p.pad, t.b);
-          tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0);
-        } else if (MODE == 1) {
-          tma_load_4d(a_dst, &tmA, &full[s], cc * KC, t.x0 + p.pad - sx, t.y0 + p.pad - r, t.b);
-          for (int g = 0; g < n_groups; ++g)
-            tma_load_3d(b_dst + g * KC * 128, &tmB, &full[s], t.n0 + g * KC, tap, cc * KC);
+          if (!skip_a) tma_load_4d(a_dst, &tmA, &full[s], cc * KC, t.x0 + sx - p.pad, t.y0 + r - p.pad, t.b);
+          if (!skip_b) tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0);
         } else {
+          if (!skip_a) {
 #pragma unroll
-          for (int g = 0; g < 128 / KC; ++g)
-            tma_load_4d(a_dst + g * KC * 128, &tmA, &full[s], t.m0 + g * KC, px0, py0, bb);
+            for (int g = 0; g < A_BOXES; ++g)
+              tma_load_4d(a_dst + g * KC * 128, &tmA, &full[s], t.m0 + g * KC, px0, py0, bb);
+          }
+          if (!skip_b) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            if (g < n_groups)
-              tma_load_4d(b_dst + g * KC * 128, &tmB, &full[s], g_ci[g], px0 + g_dx[g], py0 + g_dy[g], bb);
+            for (int g = 0; g < 8; ++g)
+              if (g < n_groups)
+                tma_load_4d(b_dst + g * KC * 128, &tmB, &full[s], g_ci[g], px0 + g_dx[g], py0 + g_dy[g], bb);
+          }
         }
         if (++s == stages) s = 0, ph ^= 1u;
         if (MODE == 2) {
@@ -329,7 +333,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 64; ++j)
               if (j < CW && j < nvalid) f[j] *= __ldg(sc + j);
           }
-          if (MODE == 1 && p.mask_ref && ok) {
+          if (p.mask_ref && ok) {
             const T* ref = reinterpret_cast<const T*>(p.mask_ref) + orow * p.ldo + nb;
             if (nvalid == CW) {
               const uint4* r4 = reinterpret_cast<const uint4*>(ref);  // 128 contiguous bytes of this thread's row
@@ -396,7 +400,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < 8; ++j) srow[j ^ (row & 7)] = q[j];
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
-        if (issuer) {
+        if (issuer && !(p.dbg & 4)) {
           if (MODE == 2) tma_reduce_add_2d(&tmO, sbuf, nb, t.m0);
           else tma_store_4d(&tmO, sbuf, nb, t.x0, t.y0, t.b);
           bulk_commit();
@@ -511,6 +515,16 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
   p.stages = stages;
   p.tmem_cols = tmem_cols_for(p.block_n);
   p.total_tiles = (int)tiles;
+  {
+    static int dbg = -1, dbg_mode = 0;
+    if (dbg < 0) {
+      const char* e = getenv("SZN_DBG");
+      dbg = e ? atoi(e) : 0;
+      e = getenv("SZN_DBG_MODE");
+      dbg_mode = e ? atoi(e) : 0;
+    }
+    p.dbg = MODE == dbg_mode ? dbg : 0;
+  }
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool attr_set = false;
   if (!attr_set) {
@@ -559,13 +573,14 @@ using namespace szn;
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
-extern "C" int szn_conv_fwd(int dtype, const void* x, const void* wt, const float* bias, void* y, int B, int H, int W,
-                            int Cin, int Cout, int R, int S, int pad, int relu, const float* scale, int scale_ld,
-                            int out_fp32, long long ldo, void* stream) {
+// shared by the forward conv and the data gradient (which is a forward conv of dY with transposed, flipped weights)
+static int conv_gemm(int dtype, const void* x, long long ldx, const void* wt, const float* bias, void* y, int B, int H,
+                     int W, int Cin, int Cout, int R, int S, int pad, int relu, const float* scale, int scale_ld,
+                     int out_fp32, long long ldo, const void* mask_ref, void* stream) {
   const int KC = dtype == SZN_BF16 ? 64 : 32;
-  if (Cin % KC && !(R == 1 && S == 1)) return set_error(SZN_ERR_ARG, "szn_conv_fwd: Cin must be a multiple of 128 bytes");
+  if (Cin % KC && !(R == 1 && S == 1)) return set_error(SZN_ERR_ARG, "conv: channels per tap must be a multiple of 128 bytes");
   int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
-  if (Ho <= 0 || Wo <= 0) return set_error(SZN_ERR_ARG, "szn_conv_fwd: empty output");
+  if (Ho <= 0 || Wo <= 0) return set_error(SZN_ERR_ARG, "conv: empty output");
   UmmaParams p{};
   p.pix_per_image = Ho * Wo;
   int Bq = B, Hq = H, Wq = W;
@@ -582,12 +597,13 @@ extern "C" int szn_conv_fwd(int dtype, const void* x, const void* wt, const floa
   p.block_n = fill_sms(p.block_n, Cout, ngran, (long long)p.tiles_x * p.tiles_y * Bq);
   p.n_tiles = ceil_div(Cout, p.block_n);
   p.ldo = ldo, p.bias = bias, p.scale = scale, p.scale_ld = scale_ld, p.relu = relu, p.out_fp32 = out_fp32;
+  p.mask_ref = mask_ref;
   CUtensorMap ta, tb, to;
   {
     long long od[4] = {Cout, Wo, Ho, Bq}, os[4] = {1, ldo, (long long)Wo * ldo, (long long)Ho * Wo * ldo};
     int obx[4] = {out_f32 ? 32 : 64, p.TW, p.TH, 1};
     if (int e = make_tmap(&to, out_f32 ? SZN_F32 : SZN_BF16, y, 4, od, os, obx)) return e;
-    long long d[4] = {Cin, Wq, Hq, Bq}, s[4] = {1, Cin, (long long)Wq * Cin, (long long)Hq * Wq * Cin};
+    long long d[4] = {Cin, Wq, Hq, Bq}, s[4] = {1, ldx, (long long)Wq * ldx, (long long)Hq * Wq * ldx};
     int bx[4] = {KC, p.TW, p.TH, 1};
     if (int e = make_tmap(&ta, dtype, x, 4, d, s, bx)) return e;
     long long K = (long long)R * S * Cin;
@@ -595,46 +611,30 @@ extern "C" int szn_conv_fwd(int dtype, const void* x, const void* wt, const floa
     int bx2[2] = {KC, p.block_n};
     if (int e = make_tmap(&tb, dtype, wt, 2, d2, s2, bx2)) return e;
   }
-  const long long grid = (long long)p.tiles_x * p.tiles_y * Bq * p.n_tiles;
-  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 0>(ta, tb, to, p, grid, (cudaStream_t)stream)
-                           : launch<float, 0>(ta, tb, to, p, grid, (cudaStream_t)stream);
+  const long long tiles = (long long)p.tiles_x * p.tiles_y * Bq * p.n_tiles;
+  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 0>(ta, tb, to, p, tiles, (cudaStream_t)stream)
+                           : launch<float, 0>(ta, tb, to, p, tiles, (cudaStream_t)stream);
 }
 
-// dx[B,H,W,Cin] (the conv input's gradient) from dy[B,Ho,Wo,Cout]; optional ReLU gate by `relu_ref` (same shape as dx)
-// and per-(image, channel) multiplier `scale`.
-extern "C" int szn_conv_dgrad(int dtype, const void* dy, const void* wt, void* dx, int B, int H, int W, int Cin,
+extern "C" int szn_conv_fwd(int dtype, const void* x, const void* wt, const float* bias, void* y, int B, int H, int W,
+                            int Cin, int Cout, int R, int S, int pad, int relu, const float* scale, int scale_ld,
+                            int out_fp32, long long ldo, void* stream) {
+  return conv_gemm(dtype, x, Cin, wt, bias, y, B, H, W, Cin, Cout, R, S, pad, relu, scale, scale_ld, out_fp32, ldo,
+                   nullptr, stream);
+}
+
+// dx[B,H,W,Cin] (the conv input's gradient) from dy[B,Ho,Wo,Cout]:
+//   dx[p, ci] = sum_{r,s,co} dy[p + pad - (r,s), co] * w[co, ci, r, s]
+//             = sum_{r',s',co} dy[p + (r',s') - (R-1-pad), co] * wt_d[ci][r',s'][co],   wt_d[ci][r'][s'][co] = w[co][ci][R-1-r'][S-1-s']
+// i.e. a forward convolution of dy with padding R-1-pad and the transposed, flipped weights that szn_pack_weight_dgrad
+// writes, so it runs on the K-major kernel path with one weight box per stage.  Epilogue: optional ReLU gate by
+// `relu_ref` (same shape as dx) and per-(image, channel) multiplier `scale`.
+extern "C" int szn_conv_dgrad(int dtype, const void* dy, const void* wt_dgrad, void* dx, int B, int H, int W, int Cin,
                               int Cout, int R, int S, int pad, const void* relu_ref, const float* scale, int scale_ld,
                               long long ld_dy, void* stream) {
-  const int KC = dtype == SZN_BF16 ? 64 : 32;
-  if (Cin % KC) return set_error(SZN_ERR_ARG, "szn_conv_dgrad: Cin must be a multiple of 128 bytes");
-  int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
-  UmmaParams p{};
-  p.pix_per_image = H * W;
-  int Bq = B, Hq = H, Wq = W;
-  if (R == 1 && S == 1 && pad == 0) Wq = B * H * W, Hq = 1, Bq = 1, Ho = 1, Wo = Wq;
-  pick_tile(Wq, Hq, 128, &p.TW, &p.TH);
-  p.tiles_x = ceil_div(Wq, p.TW), p.tiles_y = ceil_div(Hq, p.TH), p.B = Bq;
-  p.H = Hq, p.W = Wq, p.R = R, p.S = S, p.pad = pad, p.Ck = Cout, p.kchunks = ceil_div(Cout, KC);
-  p.N = Cin;
-  p.block_n = pick_block_n(Cin, KC, Cin >= 256 ? 256 : 128);
-  p.block_n = fill_sms(p.block_n, Cin, KC, (long long)p.tiles_x * p.tiles_y * Bq);
-  p.n_tiles = ceil_div(Cin, p.block_n);
-  p.ldo = Cin, p.mask_ref = relu_ref, p.scale = scale, p.scale_ld = scale_ld;
-  CUtensorMap ta, tb, to;
-  {
-    long long od[4] = {Cin, Wq, Hq, Bq}, os[4] = {1, Cin, (long long)Wq * Cin, (long long)Hq * Wq * Cin};
-    int obx[4] = {dtype == SZN_F32 ? 32 : 64, p.TW, p.TH, 1};
-    if (int e = make_tmap(&to, dtype, dx, 4, od, os, obx)) return e;
-    long long d[4] = {Cout, Wo, Ho, Bq}, s[4] = {1, ld_dy, (long long)Wo * ld_dy, (long long)Ho * Wo * ld_dy};
-    int bx[4] = {KC, p.TW, p.TH, 1};
-    if (int e = make_tmap(&ta, dtype, dy, 4, d, s, bx)) return e;
-    long long d3[3] = {Cin, (long long)R * S, Cout}, s3[3] = {1, Cin, (long long)R * S * Cin};
-    int bx3[3] = {KC, 1, KC};
-    if (int e = make_tmap(&tb, dtype, wt, 3, d3, s3, bx3, true)) return e;
-  }
-  const long long grid = (long long)p.tiles_x * p.tiles_y * Bq * p.n_tiles;
-  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 1>(ta, tb, to, p, grid, (cudaStream_t)stream)
-                           : launch<float, 1>(ta, tb, to, p, grid, (cudaStream_t)stream);
+  const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+  return conv_gemm(dtype, dy, ld_dy, wt_dgrad, nullptr, dx, B, Ho, Wo, Cout, Cin, R, S, R - 1 - pad, 0, scale, scale_ld,
+                   0, Cin, relu_ref, stream);
 }
 
 // dw[Cout][R*S*Cin] (fp32, ACCUMULATED into: the caller zeroes it) from x[B,H,W,Cin] and dy[B,Ho,Wo,Cout]

@@ -63,6 +63,15 @@ def _pack(dt, tdtype, w, o_pad=None):
     return out
 
 
+def _pack_d(dt, tdtype, w, mode=0, o_pad=None):
+    """Transposed weights for the data gradient: [Cin][R*S flipped][O_pad] (mode 0) or [R*S*Cin][O_pad] (mode 1)."""
+    O, I, R, S = w.shape
+    o_pad = O if o_pad is None else o_pad
+    out = torch.empty((I, R * S, o_pad), device=w.device, dtype=tdtype)
+    call("szn_pack_weight_dgrad", dt, ptr(w), ptr(out), O, I, R, S, o_pad, mode, _lib.stream())
+    return out
+
+
 def is_diag_bilinear(w):
     """True when ``w`` (Ci,Co,64,64) is exactly what ``_initialize_weights`` wrote (models.py:102-112)."""
     from .models import bilinear_filter
@@ -209,8 +218,10 @@ class FCN32sFunction(torch.autograd.Function):
         for n in PARAM_ORDER:
             dict.__setitem__(grads, n, None)
 
-        def packed(name):
-            return pw.cache[(name, dt)][1]
+        def packed_d(name, mode=0):
+            w = P[name + ".weight"]
+            return pw.get((name, "d", dt), (w._version, w.data_ptr()),
+                          lambda: _pack_d(dt, tdtype, w.detach().contiguous(), mode))
 
         def zeros(shape, dtype=torch.float32):
             return torch.zeros(shape, device=dev, dtype=dtype)
@@ -262,7 +273,10 @@ class FCN32sFunction(torch.autograd.Function):
 
         drop = sv["drop"]
         d7 = torch.empty((B, hs, ws, 4096), device=dev, dtype=tdtype)
-        call("szn_conv_dgrad", dt, ptr(ds17), ptr(sv["head_w"]), ptr(d7), B, hs, ws, 4096, Dp, 1, 1, 0,
+        wf, ws_ = P["score_fr.weight"], P["seenmask_score.weight"]
+        head_wd = pw.get(("head", "d", dt), (wf._version, ws_._version, wf.data_ptr()),
+                         lambda: _pack_d(dt, tdtype, torch.cat([wf.detach(), ws_.detach()], 0).contiguous(), 0, Dp))
+        call("szn_conv_dgrad", dt, ptr(ds17), ptr(head_wd), ptr(d7), B, hs, ws, 4096, Dp, 1, 1, 0,
              ptr(sv["h7"]), ptr(drop[1]) if drop is not None else None, 4096, Dp, st)
 
         def conv_backward(name, x_act, dy, xh, xw, cin, cout, k, pad, want_dx, relu_ref, scale=None):
@@ -284,7 +298,15 @@ class FCN32sFunction(torch.autograd.Function):
             if not want_dx:
                 return None
             dx = torch.empty((B, xh, xw, cin), device=dev, dtype=tdtype)
-            call("szn_conv_dgrad", dt, ptr(dy), ptr(packed(name)), ptr(dx), B, xh, xw, cin, cout, k, k, pad,
+            if k >= 5 and pad == 0 and relu_ref is None and scale is None:
+                # fc6 (7x7 valid on 23x23): one GEMM against the (tap, ci)-major transposed weights gives per-tap
+                # columns, which szn_col2im folds back; 98 full N tiles instead of 49 taps x a 512-wide N
+                dcol = torch.empty((B, ho, wo, k * k * cin), device=dev, dtype=tdtype)
+                call("szn_conv_dgrad", dt, ptr(dy), ptr(packed_d(name, 1)), ptr(dcol), B, ho, wo, k * k * cin, cout, 1, 1,
+                     0, None, None, 0, cout, st)
+                call("szn_col2im", dt, ptr(dcol), ptr(dx), B, xh, xw, cin, k, k, st)
+                return dx
+            call("szn_conv_dgrad", dt, ptr(dy), ptr(packed_d(name)), ptr(dx), B, xh, xw, cin, cout, k, k, pad,
                  ptr(relu_ref), ptr(scale), 4096 if scale is not None else 0, cout, st)
             return dx
 
