@@ -1,8 +1,8 @@
 #!/bin/bash
 # quick GPU check: kernel parity + bench kernel table
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py -q -x --timeout 120 2>&1 | tail -3
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.log 2>&1
+timeout 150 python -m pytest tests/test_kernels_gpu.py tests/test_head_gpu.py -q -x --timeout 60 2>&1 | tail -3
+timeout 150 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.log 2>&1
 python - <<PY
 import json
 l=[x for x in open('gpurun_out/bench_quick.log') if x.startswith('{')]

@@ -20,82 +20,128 @@ __device__ __forceinline__ float tent(int k) { return 1.f - fabsf((float)k - 31.
 
 // ------------------------------------------------------------------------------------------------
 // upscore with the diagonal bilinear weight == per-channel x32 bilinear upsample, cropped at 19.
-// s: [B,hs,ws,ld] fp32 (channels coff..coff+D) -> out: NCHW fp32 [B,D,H,W]. One thread = 4 consecutive X.
+// s: [B,hs,ws,ld] fp32 (channels coff..coff+D) -> out: NCHW fp32 [B,D,H,W].
+// HBM-bound on the write of out (B*D*H*W*4 bytes).  One CTA = one (b, d) plane x UP_ROWS output rows: the plane's
+// hs x ws source values sit zero-padded in shared memory (no border branches), each thread produces VEC consecutive
+// X per row (16-byte coalesced stores) from 3 vertically interpolated source columns.
 // ------------------------------------------------------------------------------------------------
+constexpr int UP_ROWS = 64;
+constexpr int UP_MAXSRC = 34;  // hs, ws <= 32 (inputs up to ~900 px); larger maps use more shared memory than we reserve
+
 template <int VEC>
-__global__ void upsample_fwd_kernel(const float* __restrict__ s, float* __restrict__ out, int B, int D, int H, int W,
-                                    int hs, int ws, int ld, int coff) {
+__global__ void __launch_bounds__(128) upsample_fwd_kernel(const float* __restrict__ s, float* __restrict__ out, int B, int D,
+                                                           int H, int W, int hs, int ws, int ld, int coff) {
+  __shared__ float sp[UP_MAXSRC][UP_MAXSRC + 1];  // sp[i+1][j+1] = s[i][j], zero border
+  const int plane = blockIdx.x;                   // b * D + d
+  const int b = plane / D, d = plane - b * D;
+  const int y_begin = blockIdx.y * UP_ROWS;
+  for (int i = threadIdx.x; i < (hs + 2) * (ws + 2); i += blockDim.x) {
+    const int r = i / (ws + 2), c = i - r * (ws + 2);
+    float v = 0.f;
+    if (r >= 1 && r <= hs && c >= 1 && c <= ws) v = s[(((long long)b * hs + (r - 1)) * ws + (c - 1)) * ld + coff + d];
+    sp[r][c] = v;
+  }
+  __syncthreads();
+  float* oplane = out + (long long)plane * H * W;
   const int wv = (W + VEC - 1) / VEC;
-  const long long total = (long long)B * D * H * wv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int xq = (int)(i % wv);
-    long long r = i / wv;
-    const int Y = (int)(r % H);
-    r /= H;
-    const int d = (int)(r % D);
-    const int b = (int)(r / D);
-    const int u = Y + UPCROP;
-    const int iy1 = u >> 5, ky1 = u & 31;
-    const float fy1 = tent(ky1), fy0 = tent(ky1 + 32);
-    const float* sb = s + (long long)b * hs * ws * ld + coff + d;
-    float o[VEC];
+  for (int xq = threadIdx.x; xq < wv; xq += blockDim.x) {
+    // horizontal taps of this thread's VEC pixels: source columns ix1 (weight fx1) and ix1-1 (weight fx0)
+    int cb = ((xq * VEC + UPCROP) >> 5);  // padded index of column ix1-1 for the first pixel
+    float fx1[VEC], fx0[VEC];
+    int sel[VEC];  // 0: columns (cb, cb+1), 1: columns (cb+1, cb+2)
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      const int X = xq * VEC + j;
-      const int v = X + UPCROP;
-      const int ix1 = v >> 5, kx1 = v & 31;
-      const float fx1 = tent(kx1), fx0 = tent(kx1 + 32);
-      float acc = 0.f;
-      if (iy1 < hs) {
-        if (ix1 < ws) acc += sb[((long long)iy1 * ws + ix1) * ld] * (fy1 * fx1);
-        if (ix1 >= 1) acc += sb[((long long)iy1 * ws + ix1 - 1) * ld] * (fy1 * fx0);
-      }
-      if (iy1 >= 1) {
-        if (ix1 < ws) acc += sb[((long long)(iy1 - 1) * ws + ix1) * ld] * (fy0 * fx1);
-        if (ix1 >= 1) acc += sb[((long long)(iy1 - 1) * ws + ix1 - 1) * ld] * (fy0 * fx0);
-      }
-      o[j] = acc;
+      const int v = xq * VEC + j + UPCROP;
+      sel[j] = (v >> 5) - cb;
+      fx1[j] = tent(v & 31), fx0[j] = tent((v & 31) + 32);
     }
-    float* dst = out + (((long long)b * D + d) * H + Y) * W + (long long)xq * VEC;
-    if (VEC == 4) {
-      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-    } else {
-      dst[0] = o[0];
+    int y_end = y_begin + UP_ROWS;
+    if (y_end > H) y_end = H;
+    for (int Y = y_begin; Y < y_end; ++Y) {
+      const int u = Y + UPCROP;
+      const int r0 = u >> 5;  // padded row index of iy1-1; iy1 is r0+1
+      const float fy1 = tent(u & 31), fy0 = tent((u & 31) + 32);
+      const float v0 = fy1 * sp[r0 + 1][cb] + fy0 * sp[r0][cb];
+      const float v1 = fy1 * sp[r0 + 1][cb + 1] + fy0 * sp[r0][cb + 1];
+      const float v2 = fy1 * sp[r0 + 1][cb + 2] + fy0 * sp[r0][cb + 2];
+      float o[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = sel[j] ? (fx1[j] * v2 + fx0[j] * v1) : (fx1[j] * v1 + fx0[j] * v0);
+      float* dst = oplane + (long long)Y * W + xq * VEC;
+      if (VEC == 4) {
+        __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+      } else {
+        dst[0] = o[0];
+      }
     }
   }
 }
 
 // transpose of the above: ds[b,iy,ix,coff+d] = sum_{ky,kx} g[b,d,32iy+ky-19,32ix+kx-19] f(ky) f(kx).
-// One CTA per (b, d, iy): column sums over the 64 contributing rows (coalesced row reads), then 64-tap row sums.
+// HBM-bound on the read of g.  One CTA per (b, d) plane streams its H rows ONCE (coalesced, 8 rows in flight per
+// thread): a row feeds source row iy1 with weight f(ky) and iy1-1 with f(ky+32); when a 32-row group ends, the finished
+// column sums are folded along x by 8 threads per ix (64 taps each).
 template <typename T>
-__global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ g, T* __restrict__ ds, int B, int D,
+__global__ void __launch_bounds__(512) upsample_bwd_kernel(const float* __restrict__ g, T* __restrict__ ds, int B, int D,
                                                            int H, int W, int hs, int ws, int ld, int coff) {
   extern __shared__ float col[];  // [W]
-  const int iy = blockIdx.x % hs;
-  const int d = (blockIdx.x / hs) % D;
-  const int b = blockIdx.x / (hs * D);
-  const float* gb = g + ((long long)b * D + d) * H * W;
-  for (int X = threadIdx.x; X < W; X += 256) {
-    float acc = 0.f;
-    for (int ky = 0; ky < UPK; ++ky) {
-      const int Y = UPS * iy + ky - UPCROP;
-      if (Y >= 0 && Y < H) acc = fmaf(gb[(long long)Y * W + X], tent(ky), acc);
+  const int plane = blockIdx.x;
+  const int b = plane / D, d = plane - b * D;
+  const float* gp = g + (long long)plane * H * W;
+  constexpr int NC = 2;  // columns per thread (W <= 1024)
+  float carry[NC], accA[NC], accB[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) carry[c] = accA[c] = accB[c] = 0.f;
+  const int n_groups = (H + UPCROP + 31) >> 5;  // groups of rows with the same iy1 = (Y + 19) >> 5
+  for (int k = 0; k <= n_groups; ++k) {
+    // rows of group k: u = Y + 19 in [32k, 32k + 31]
+    if (k < n_groups) {
+      int y0 = 32 * k - UPCROP, y1 = y0 + 32;
+      if (y0 < 0) y0 = 0;
+      if (y1 > H) y1 = H;
+#pragma unroll 8
+      for (int Y = y0; Y < y1; ++Y) {
+        const int ky = (Y + UPCROP) & 31;
+        const float fy1 = tent(ky), fy0 = tent(ky + 32);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int X = threadIdx.x + c * 512;
+          if (X < W) {
+            const float v = __ldcs(gp + (long long)Y * W + X);
+            accA[c] = fmaf(v, fy1, accA[c]);
+            accB[c] = fmaf(v, fy0, accB[c]);
+          }
+        }
+      }
     }
-    col[X] = acc;
-  }
-  __syncthreads();
-  // 8 threads per ix cooperate on the 64 taps
-  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
-  for (int ix = grp; ix < ws; ix += 32) {
-    float acc = 0.f;
-    for (int kx = sub; kx < UPK; kx += 8) {
-      const int X = UPS * ix + kx - UPCROP;
-      if (X >= 0 && X < W) acc = fmaf(col[X], tent(kx), acc);
+    // source row iy = k - 1 is complete: carry (its f(ky) part from group k-1) + accB (its f(ky+32) part from group k)
+    const int iy = k - 1;
+    if (iy >= 0 && iy < hs) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int X = threadIdx.x + c * 512;
+        if (X < W) col[X] = carry[c] + accB[c];
+      }
+      __syncthreads();
+      const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;  // 64 groups of 8 threads
+      for (int ix0 = 0; ix0 < ws; ix0 += 64) {  // warp-uniform trip count: every lane takes part in the shuffles
+        const int ix = ix0 + grp;
+        float acc = 0.f;
+        if (ix < ws) {
+          for (int kx = sub; kx < UPK; kx += 8) {
+            const int X = UPS * ix + kx - UPCROP;
+            if (X >= 0 && X < W) acc = fmaf(col[X], tent(kx), acc);
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (sub == 0 && ix < ws) ds[(((long long)b * hs + iy) * ws + ix) * ld + coff + d] = hfrom_float<T>(acc);
+      }
+      __syncthreads();
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    if (sub == 0) ds[(((long long)b * hs + iy) * ws + ix) * ld + coff + d] = hfrom_float<T>(acc);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) carry[c] = accA[c], accA[c] = 0.f, accB[c] = 0.f;
   }
 }
 
@@ -213,79 +259,150 @@ __device__ __forceinline__ void block_accumulate(double a, double b, double* acc
   }
 }
 
-template <int KIND>
+template <int VEC>
+struct PixVec {
+  float v[VEC];
+};
+template <int VEC>
+__device__ __forceinline__ PixVec<VEC> ld_pix(const float* p) {
+  PixVec<VEC> r;
+  if (VEC == 4) {
+    const float4 f = __ldcs(reinterpret_cast<const float4*>(p));
+    r.v[0] = f.x, r.v[1 % VEC] = f.y, r.v[2 % VEC] = f.z, r.v[3 % VEC] = f.w;
+  } else {
+    r.v[0] = __ldcs(p);
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void st_pix(float* p, const PixVec<VEC>& r) {
+  if (VEC == 4) __stcs(reinterpret_cast<float4*>(p), make_float4(r.v[0], r.v[1 % VEC], r.v[2 % VEC], r.v[3 % VEC]));
+  else __stcs(p, r.v[0]);
+}
+
+// One thread = VEC consecutive pixels of one image (VEC = 4: 16-byte loads of every channel plane, fully coalesced),
+// channel loop unrolled 4x so 4-8 independent 16-byte loads per thread are in flight: HBM-bound, one pass over score.
+template <int KIND, int VEC>
 __global__ void __launch_bounds__(256) embed_loss_fwd_kernel(const float* __restrict__ score, const long long* __restrict__ target,
                                                              const float* __restrict__ te, const float* __restrict__ table,
                                                              int n, int c, long long hw, float* __restrict__ stats,
                                                              double* __restrict__ accum) {
-  const long long total = n * hw;
+  const long long total = n * hw / VEC;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   double part = 0, cnt = 0;
   if (i < total) {
-    const long long t = target[i];
-    if (t >= 0) {
-      const long long b = i / hw, p = i - b * hw;
+    const long long pix = i * VEC;  // hw % VEC == 0: the VEC pixels share one image
+    const long long b = pix / hw, p = pix - b * hw;
+    long long t[VEC];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) t[j] = target[pix + j], any |= t[j] >= 0;
+    if (any) {
       const float* sp = score + b * c * hw + p;
       const float* ep = te ? te + b * c * hw + p : nullptr;
-      const float* tp = table ? table + t * c : nullptr;
-      float ss = 0.f, se = 0.f, ee = 0.f, sq = 0.f;
+      const float* tp[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) tp[j] = table ? table + (t[j] >= 0 ? t[j] : 0) * c : nullptr;
+      float ss[VEC], se[VEC], ee[VEC], sq[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) ss[j] = se[j] = ee[j] = sq[j] = 0.f;
 #pragma unroll 4
       for (int d = 0; d < c; ++d) {
-        const float s = sp[d * hw];
-        const float e = ep ? ep[d * hw] : __ldg(tp + d);
-        if (KIND == 0) {
-          ss = fmaf(s, s, ss);
-          se = fmaf(s, e, se);
-          ee = fmaf(e, e, ee);
+        const PixVec<VEC> sv = ld_pix<VEC>(sp + d * hw);
+        PixVec<VEC> ev;
+        if (ep) {
+          ev = ld_pix<VEC>(ep + d * hw);
         } else {
-          const float df = s - e;
-          sq = fmaf(df, df, sq);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) ev.v[j] = __ldg(tp[j] + d);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          if (KIND == 0) {
+            ss[j] = fmaf(sv.v[j], sv.v[j], ss[j]);
+            se[j] = fmaf(sv.v[j], ev.v[j], se[j]);
+            ee[j] = fmaf(ev.v[j], ev.v[j], ee[j]);
+          } else {
+            const float df = sv.v[j] - ev.v[j];
+            sq[j] = fmaf(df, df, sq[j]);
+          }
         }
       }
-      if (KIND == 0) {
-        const float inv_s = 1.f / sqrtf(ss), inv_e = 1.f / sqrtf(ee);
-        const float cs = se * inv_s * inv_e;
-        stats[3 * i] = inv_s, stats[3 * i + 1] = inv_e, stats[3 * i + 2] = cs;
-        part = cs;
-      } else {
-        part = sq;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        if (t[j] < 0) continue;
+        if (KIND == 0) {
+          const float inv_s = 1.f / sqrtf(ss[j]), inv_e = 1.f / sqrtf(ee[j]);
+          const float cs = se[j] * inv_s * inv_e;
+          float* st = stats + 3 * (pix + j);
+          st[0] = inv_s, st[1] = inv_e, st[2] = cs;
+          part += cs;
+        } else {
+          part += sq[j];
+        }
+        cnt += 1;
       }
-      cnt = 1;
     }
   }
   block_accumulate(part, cnt, accum);
 }
 
-template <int KIND>
+template <int KIND, int VEC>
 __global__ void __launch_bounds__(256) embed_loss_bwd_kernel(const float* __restrict__ score, const long long* __restrict__ target,
                                                              const float* __restrict__ te, const float* __restrict__ table,
                                                              int n, int c, long long hw, const float* __restrict__ stats,
                                                              const double* __restrict__ accum, const float* __restrict__ gout,
                                                              float* __restrict__ dscore) {
-  const long long total = n * hw;
+  const long long total = n * hw / VEC;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const long long t = target[i];
-  const long long b = i / hw, p = i - b * hw;
+  const long long pix = i * VEC;
+  const long long b = pix / hw, p = pix - b * hw;
+  long long t[VEC];
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) t[j] = target[pix + j], any |= t[j] >= 0;
   float* gp = dscore + b * c * hw + p;
-  if (t < 0) {
-    for (int d = 0; d < c; ++d) gp[d * hw] = 0.f;
+  if (!any) {
+    PixVec<VEC> z;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) z.v[j] = 0.f;
+    for (int d = 0; d < c; ++d) st_pix<VEC>(gp + d * hw, z);
     return;
   }
   const float gs = gout[0] / (float)accum[1];
   const float* sp = score + b * c * hw + p;
   const float* ep = te ? te + b * c * hw + p : nullptr;
-  const float* tp = table ? table + t * c : nullptr;
-  float inv_s = 0, inv_e = 0, cs = 0;
-  if (KIND == 0) inv_s = stats[3 * i], inv_e = stats[3 * i + 1], cs = stats[3 * i + 2];
+  const float* tp[VEC];
+  float inv_s[VEC], inv_e[VEC], cs[VEC], live[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    tp[j] = table ? table + (t[j] >= 0 ? t[j] : 0) * c : nullptr;
+    live[j] = t[j] >= 0 ? 1.f : 0.f;
+    inv_s[j] = inv_e[j] = cs[j] = 0.f;
+    if (KIND == 0 && t[j] >= 0) {
+      const float* st = stats + 3 * (pix + j);
+      inv_s[j] = st[0], inv_e[j] = st[1], cs[j] = st[2];
+    }
+  }
 #pragma unroll 4
   for (int d = 0; d < c; ++d) {
-    const float s = sp[d * hw];
-    const float e = ep ? ep[d * hw] : __ldg(tp + d);
-    float g;
-    if (KIND == 0) g = -gs * (e * inv_e - cs * s * inv_s) * inv_s;  // d(-cos)/ds
-    else g = 2.f * gs * (s - e);
-    gp[d * hw] = g;
+    const PixVec<VEC> sv = ld_pix<VEC>(sp + d * hw);
+    PixVec<VEC> ev, gv;
+    if (ep) {
+      ev = ld_pix<VEC>(ep + d * hw);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) ev.v[j] = __ldg(tp[j] + d);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float g;
+      if (KIND == 0) g = -gs * (ev.v[j] * inv_e[j] - cs[j] * sv.v[j] * inv_s[j]) * inv_s[j];  // d(-cos)/ds
+      else g = 2.f * gs * (sv.v[j] - ev.v[j]);
+      gv.v[j] = live[j] != 0.f ? g : 0.f;
+    }
+    st_pix<VEC>(gp + d * hw, gv);
   }
 }
 
@@ -475,25 +592,24 @@ using namespace szn;
 
 extern "C" int szn_upsample32_crop_fwd(const float* s, float* out, int B, int D, int H, int W, int hs, int ws, int ld,
                                        int coff, void* stream) {
-  if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    const long long total = (long long)B * D * H * (W / 4);
-    upsample_fwd_kernel<4><<<hgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(s, out, B, D, H, W, hs, ws, ld, coff);
-  } else {
-    const long long total = (long long)B * D * H * W;
-    upsample_fwd_kernel<1><<<hgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(s, out, B, D, H, W, hs, ws, ld, coff);
-  }
+  if (hs + 2 > UP_MAXSRC || ws + 2 > UP_MAXSRC) return set_error(SZN_ERR_UNSUPPORTED, "szn_upsample32_crop_fwd: map too large");
+  const dim3 grid((unsigned)((long long)B * D), (unsigned)((H + UP_ROWS - 1) / UP_ROWS));
+  if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    upsample_fwd_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(s, out, B, D, H, W, hs, ws, ld, coff);
+  else
+    upsample_fwd_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(s, out, B, D, H, W, hs, ws, ld, coff);
   return check_launch("szn_upsample32_crop_fwd");
 }
 
 extern "C" int szn_upsample32_crop_bwd(int dtype, const float* g, void* ds, int B, int D, int H, int W, int hs, int ws,
                                        int ld, int coff, void* stream) {
-  const unsigned grid = (unsigned)((long long)B * D * hs);
+  const unsigned grid = (unsigned)((long long)B * D);
   const size_t smem = (size_t)W * sizeof(float);
-  if (smem > 48 * 1024) return set_error(SZN_ERR_UNSUPPORTED, "szn_upsample32_crop_bwd: W too large");
+  if (W > 1024) return set_error(SZN_ERR_UNSUPPORTED, "szn_upsample32_crop_bwd: W too large");
   if (dtype == SZN_BF16)
-    upsample_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(g, (__nv_bfloat16*)ds, B, D, H, W, hs, ws, ld, coff);
+    upsample_bwd_kernel<__nv_bfloat16><<<grid, 512, smem, (cudaStream_t)stream>>>(g, (__nv_bfloat16*)ds, B, D, H, W, hs, ws, ld, coff);
   else
-    upsample_bwd_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(g, (float*)ds, B, D, H, W, hs, ws, ld, coff);
+    upsample_bwd_kernel<float><<<grid, 512, smem, (cudaStream_t)stream>>>(g, (float*)ds, B, D, H, W, hs, ws, ld, coff);
   return check_launch("szn_upsample32_crop_bwd");
 }
 
@@ -531,10 +647,13 @@ extern "C" int szn_embed_loss_fwd(int kind, const float* score, const long long*
   cudaStream_t st = (cudaStream_t)stream;
   const long long hw = (long long)h * w, total = n * hw;
   cudaMemsetAsync(accum, 0, 2 * sizeof(double), st);
-  const unsigned grid = (unsigned)((total + 255) / 256);
-  if (kind == 0) embed_loss_fwd_kernel<0><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum);
-  else if (kind == 1) embed_loss_fwd_kernel<1><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum);
-  else return set_error(SZN_ERR_ARG, "szn_embed_loss_fwd: kind");
+  if (kind != 0 && kind != 1) return set_error(SZN_ERR_ARG, "szn_embed_loss_fwd: kind");
+  const bool v4 = hw % 4 == 0 && ((reinterpret_cast<uintptr_t>(score) | reinterpret_cast<uintptr_t>(target_embed)) & 15) == 0;
+  const unsigned grid = (unsigned)((total / (v4 ? 4 : 1) + 255) / 256);
+  if (kind == 0 && v4) embed_loss_fwd_kernel<0, 4><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum);
+  else if (kind == 0) embed_loss_fwd_kernel<0, 1><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum);
+  else if (v4) embed_loss_fwd_kernel<1, 4><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum);
+  else embed_loss_fwd_kernel<1, 1><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum);
   if (int e = check_launch("szn_embed_loss_fwd")) return e;
   loss_finalize_kernel<<<1, 1, 0, st>>>(accum, kind, loss);
   return check_launch("szn_embed_loss_fwd/finalize");
@@ -550,12 +669,14 @@ extern "C" int szn_embed_loss_bwd(int kind, const float* score, const long long*
                                   const double* accum, const float* grad_out, float* dscore, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const long long hw = (long long)h * w, total = n * hw;
-  const unsigned grid = (unsigned)((total + 255) / 256);
-  if (kind == 0)
-    embed_loss_bwd_kernel<0><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum, grad_out, dscore);
-  else if (kind == 1)
-    embed_loss_bwd_kernel<1><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum, grad_out, dscore);
-  else return set_error(SZN_ERR_ARG, "szn_embed_loss_bwd: kind");
+  if (kind != 0 && kind != 1) return set_error(SZN_ERR_ARG, "szn_embed_loss_bwd: kind");
+  const bool v4 = hw % 4 == 0 && ((reinterpret_cast<uintptr_t>(score) | reinterpret_cast<uintptr_t>(target_embed) |
+                                   reinterpret_cast<uintptr_t>(dscore)) & 15) == 0;
+  const unsigned grid = (unsigned)((total / (v4 ? 4 : 1) + 255) / 256);
+  if (kind == 0 && v4) embed_loss_bwd_kernel<0, 4><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum, grad_out, dscore);
+  else if (kind == 0) embed_loss_bwd_kernel<0, 1><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum, grad_out, dscore);
+  else if (v4) embed_loss_bwd_kernel<1, 4><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum, grad_out, dscore);
+  else embed_loss_bwd_kernel<1, 1><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum, grad_out, dscore);
   return check_launch("szn_embed_loss_bwd");
 }
 

@@ -32,14 +32,20 @@ class GradientAllReduce:
     def _on_ready(self, name, g):
         nbytes = g.numel() * g.element_size()
         self.bytes_reduced += nbytes
-        if nbytes < self.small_bytes or not g.is_contiguous():
+        if nbytes < self.small_bytes:
             self.small.append(g)
             return
+        if not g.is_contiguous():
+            # conv weight gradients are OIHW-shaped views of a dense [O][R][S][I] buffer: reduce that buffer in place
+            g = g.permute(0, 2, 3, 1)
+            if not g.is_contiguous():
+                self.small.append(g.permute(0, 3, 1, 2))
+                return
         self.works.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def _flush(self):
         if self.small:
-            flat = torch.cat([g.reshape(-1) for g in self.small])
+            flat = torch.cat([g.reshape(-1) for g in self.small])  # reshape copies the few strided ones
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
             off = 0
             for g in self.small:

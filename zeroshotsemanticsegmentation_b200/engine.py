@@ -56,6 +56,7 @@ class PackedWeights:
 
 
 def _pack(dt, tdtype, w, o_pad=None):
+    w = w.contiguous()  # parameters may be channels_last (models._use_kernel_weight_layout); the pack kernels read OIHW
     O, I, R, S = w.shape
     o_pad = O if o_pad is None else o_pad
     out = torch.empty((o_pad, R * S, I), device=w.device, dtype=tdtype)
@@ -65,6 +66,7 @@ def _pack(dt, tdtype, w, o_pad=None):
 
 def _pack_d(dt, tdtype, w, mode=0, o_pad=None):
     """Transposed weights for the data gradient: [Cin][R*S flipped][O_pad] (mode 0) or [R*S*Cin][O_pad] (mode 1)."""
+    w = w.contiguous()
     O, I, R, S = w.shape
     o_pad = O if o_pad is None else o_pad
     out = torch.empty((I, R * S, o_pad), device=w.device, dtype=tdtype)
@@ -111,6 +113,7 @@ class FCN32sFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, x, *params):
+        ctx.set_materialize_grads(False)  # an unused head (mode='fcn' / 'seenmask') arrives as None, not as zeros
         dt, tdtype = PRECISIONS[module.precision]
         st = _lib.stream()
         dev = x.device
@@ -227,6 +230,8 @@ class FCN32sFunction(torch.autograd.Function):
             return torch.zeros(shape, device=dev, dtype=dtype)
 
         # ---------------- heads: d s17 ----------------
+        if gf is None and gs is None:
+            return _finish(module, grads)
         ds17 = zeros((B, hs, ws, Dp), tdtype)
         if gf is not None:
             gf = gf.contiguous()
@@ -285,12 +290,9 @@ class FCN32sFunction(torch.autograd.Function):
             if need[name + ".weight"]:
                 dw = zeros((cout, k * k, cin))
                 call("szn_conv_wgrad", dt, ptr(x_act), ptr(dy), ptr(dw), B, xh, xw, cin, cout, k, k, pad, cout, st)
-                if k == 1:
-                    grads[name + ".weight"] = dw.reshape(cout, cin, 1, 1)
-                else:
-                    g = torch.empty((cout, cin, k, k), device=dev, dtype=torch.float32)
-                    call("szn_unpack_wgrad", ptr(dw), ptr(g), cout, cin, k, k, st)
-                    grads[name + ".weight"] = g
+                # dW lives as [Cout][R][S][Cin]; hand autograd the OIHW-shaped *view* of it (channels_last strides):
+                # same values, no unpack pass over 135 M gradients
+                grads[name + ".weight"] = dw.view(cout, k, k, cin).permute(0, 3, 1, 2)
             if need[name + ".bias"]:
                 db = zeros((cout,))
                 call("szn_bias_grad", dt, ptr(dy), ptr(db), B * ho * wo, cout, cout, st)

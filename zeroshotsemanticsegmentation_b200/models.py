@@ -69,6 +69,7 @@ class FCN32s(nn.Module):
         self.seenmask_score = nn.Conv2d(4096, 2, 1)
         self.seenmask_upscore = nn.ConvTranspose2d(2, 2, 64, stride=32, bias=False)
         self._initialize_weights()
+        self._use_kernel_weight_layout()
         self._packed = engine.PackedWeights()
         self._grad_ready = None   # data-parallel hook: fn(name, grad) called as each gradient is final (ddp.py)
         self._grad_flush = None   # data-parallel hook: fn() called once at the end of backward
@@ -81,6 +82,14 @@ class FCN32s(nn.Module):
                 assert m.kernel_size[0] == m.kernel_size[1]
                 with torch.no_grad():
                     m.weight.copy_(get_upsampling_weight(m.in_channels, m.out_channels, m.kernel_size[0]))
+
+    def _use_kernel_weight_layout(self):
+        """Keep every k>1 conv weight in channels_last memory ([O][R][S][I] dense; shape, values and state_dict are
+        unchanged).  That is the layout the wgrad kernel writes, so ``weight.grad`` is adopted by autograd as a view of
+        the kernel's output buffer instead of being transposed through an extra pass over 135 M gradients."""
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d) and m.kernel_size[0] > 1 and m.in_channels > 3:
+                m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
 
     def _ordered_params(self):
         sd = dict(self.named_parameters())
