@@ -36,7 +36,7 @@ struct UmmaParams {
   int Cin;      // MODE 2: channels per tap inside the N index
   int block_n, n_tiles, m_tiles, stages, splits, tmem_cols;
   int total_tiles;  // n_tiles * m_tiles (* splits): work items of the persistent tile loop
-  int zero_smem;
+  int gpt, b_boxes, ksteps;  // MODE 2: 128-byte column groups per B box, B boxes per stage, MMAs (K steps) per stage
   int dbg;  // timing experiments only (SZN_DBG / SZN_DBG_MODE env): bit0 skip A loads, bit1 skip B loads
   long long ldo;          // row stride of the output, elements (mask_ref shares it)
   const float* bias;      // [N] or null
@@ -124,12 +124,6 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (p.zero_smem) {
-    uint4* z = reinterpret_cast<uint4*>(smem);
-    const int n16 = stages * stage_bytes / 16;
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async_smem();
-  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -162,31 +156,35 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // =========================== TMA producer ===========================
     // One thread; all index decompositions inside a tile are carried incrementally (a runtime integer division costs
     // ~100 cycles; 19 of them per wgrad stage made the producer the bottleneck in the first profile).
-    constexpr int A_BOXES = (MODE == 2) ? 128 / KC : 1;
-    const int n_groups = block_n / KC;
-    const uint32_t a_tx = (uint32_t)(A_BOXES * rows_a * 128);
-    const uint32_t b_tx = (MODE == 2) ? (uint32_t)(n_groups * rows_a * 128) : (uint32_t)(block_n * 128);
+    // MODE 2 operands are fetched with 5-D boxes {KC channels, TW, TH, 1, G channel groups}: one box lands G column
+    // groups (each rows_a x 128 B, back to back) instead of one 4 KB box per group -- the TMA unit pays a fixed cost per
+    // box, and twelve small boxes per stage made the wgrad load-bound.
+    const uint32_t a_tx = (MODE == 2) ? (uint32_t)((128 / KC) * rows_a * 128) : (uint32_t)(rows_a * 128);
+    const uint32_t box_tx = (uint32_t)(p.gpt * rows_a * 128);  // MODE 2: bytes of one B box
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<MODE>(p, tile);
       int tap = 0, cc = 0, r = 0, sx = 0;  // MODE 0: filter tap (r, sx) and channel chunk
       int bb = 0, py0 = 0, px0 = 0;        // MODE 2: pixel chunk (image, tile origin)
-      int g_ci[8], g_dx[8], g_dy[8];       // MODE 2: per 128-byte column group: channel offset and tap shift
+      int g_cg[4], g_dx[4], g_dy[4];       // MODE 2: per B box: first channel group and tap shift
+      int n_bbox = 0;                      // MODE 2: boxes of this tile that lie inside the filter (last N tile may be short)
       if (MODE == 2) {
         const int bq = t.q_begin / tiles_per_img;
         const int tt = t.q_begin - bq * tiles_per_img;
         const int ty = tt / p.tiles_x;
         bb = bq, py0 = ty * p.TH, px0 = (tt - ty * p.tiles_x) * p.TW;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int nn = t.n0 + g * KC;
+        for (int j = 0; j < 4; ++j) {
+          const int nn = t.n0 + j * p.gpt * KC;
           const int tp = nn / p.Cin;
-          g_ci[g] = nn - tp * p.Cin;
+          g_cg[j] = (nn - tp * p.Cin) / KC;
           const int rr = tp / p.S;
-          g_dy[g] = rr - p.pad, g_dx[g] = tp - rr * p.S - p.pad;
+          g_dy[j] = rr - p.pad, g_dx[j] = tp - rr * p.S - p.pad;
+          if (j < p.b_boxes && tp < p.R * p.S) n_bbox = j + 1;
         }
       }
+      const uint32_t b_tx = (MODE == 2) ? (uint32_t)n_bbox * box_tx : (uint32_t)(block_n * 128);
       for (int it = 0; it < t.n_iters; ++it) {
         mbar_wait(&empty[s], ph ^ 1u);
         uint8_t* a_dst = smem + s * stage_bytes;
@@ -199,16 +197,12 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!skip_a) tma_load_4d(a_dst, &tmA, &full[s], cc * KC, t.x0 + sx - p.pad, t.y0 + r - p.pad, t.b);
           if (!skip_b) tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0);
         } else {
-          if (!skip_a) {
-#pragma unroll
-            for (int g = 0; g < A_BOXES; ++g)
-              tma_load_4d(a_dst + g * KC * 128, &tmA, &full[s], t.m0 + g * KC, px0, py0, bb);
-          }
+          if (!skip_a) tma_load_5d(a_dst, &tmA, &full[s], 0, px0, py0, bb, t.m0 / KC);
           if (!skip_b) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              if (g < n_groups)
-                tma_load_4d(b_dst + g * KC * 128, &tmB, &full[s], g_ci[g], px0 + g_dx[g], py0 + g_dy[g], bb);
+            for (int j = 0; j < 4; ++j)
+              if (j < n_bbox)
+                tma_load_5d(b_dst + j * box_tx, &tmB, &full[s], 0, px0 + g_dx[j], py0 + g_dy[j], bb, g_cg[j]);
           }
         }
         if (++s == stages) s = 0, ph ^= 1u;
@@ -245,16 +239,17 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint32_t b_addr = a_addr + A_BYTES;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // K-major: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzled row.
-          // MN-major: 128 B-wide groups KC*128 B apart (LBO), K advances UK rows of 128 B; the K rows come in groups
-          // SBO apart: 8 rows / 1024 B for 16-bit operands (SWIZZLE_128B), 4 rows / 512 B for tf32
-          // (SWIZZLE_128B_BASE32B, the only MN-major layout tcgen05 takes for 32-bit operands).
-          constexpr uint32_t MN_LAYOUT = TF32 ? 1u : 2u, MN_SBO = TF32 ? 512u : 1024u;
-          const uint64_t adesc = A_MN ? umma_desc(a_addr + k * UK * 128, KC * 128, MN_SBO, MN_LAYOUT)
+        // K-major: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzled row.
+        // MN-major: 128 B-wide column groups LBO = rows_a*128 B apart (as the 5-D TMA box lays them down), K advances UK
+        // rows of 128 B per MMA; the K rows come in groups SBO apart: 8 rows / 1024 B for 16-bit operands (SWIZZLE_128B),
+        // 4 rows / 512 B for tf32 (SWIZZLE_128B_BASE32B, the only MN-major layout tcgen05 takes for 32-bit operands).
+        constexpr uint32_t MN_LAYOUT = TF32 ? 1u : 2u, MN_SBO = TF32 ? 512u : 1024u;
+        const uint32_t lbo = (uint32_t)rows_a * 128u;
+        const int ksteps = (MODE == 2) ? p.ksteps : 4;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t adesc = A_MN ? umma_desc(a_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
                                       : umma_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t bdesc = B_MN ? umma_desc(b_addr + k * UK * 128, KC * 128, MN_SBO, MN_LAYOUT)
+          const uint64_t bdesc = B_MN ? umma_desc(b_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
                                       : umma_desc_sw128(b_addr + k * 32, 16, 1024);
           tc_mma<TF32>(dacc, adesc, bdesc, idesc, (uint32_t)((it | k) != 0));
         }
@@ -638,21 +633,53 @@ extern "C" int szn_conv_dgrad(int dtype, const void* dy, const void* wt_dgrad, v
 }
 
 // dw[Cout][R*S*Cin] (fp32, ACCUMULATED into: the caller zeroes it) from x[B,H,W,Cin] and dy[B,Ho,Wo,Cout]
+// K-chunk shape of the wgrad: TW x TH pixels with TW*TH <= max_rows and a multiple of the UMMA K step, minimising the
+// padded pixel count over a W x H image (ties: wider)
+static void pick_tile_k(int W, int H, int max_rows, int step, int* TW, int* TH) {
+  long long best = -1;
+  int bw = step, bh = 1;
+  for (int tw = 1; tw <= max_rows; ++tw) {
+    for (int th = max_rows / tw; th >= 1; --th) {
+      if ((tw * th) % step) continue;
+      const long long cost = (long long)ceil_div(W, tw) * ceil_div(H, th) * tw * th;
+      if (best < 0 || cost < best || (cost == best && tw > bw)) best = cost, bw = tw, bh = th;
+      break;  // smaller th for the same tw only helps through `cost`, examined via other tw
+    }
+  }
+  *TW = bw;
+  *TH = bh;
+}
+
 extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* dw, int B, int H, int W, int Cin,
                               int Cout, int R, int S, int pad, long long ld_dy, void* stream) {
-  const int KC = dtype == SZN_BF16 ? 64 : 32;
-  if (Cin % KC) return set_error(SZN_ERR_ARG, "szn_conv_wgrad: Cin must be a multiple of 128 bytes");
+  const int KC = dtype == SZN_BF16 ? 64 : 32, UK = KC / 4;
+  if (Cin % KC || Cout % KC || ld_dy % KC)
+    return set_error(SZN_ERR_ARG, "szn_conv_wgrad: Cin, Cout and ld_dy must be multiples of 128 bytes");
   int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
   int Bq = B, Hq = H, Wq = W;
   if (R == 1 && S == 1 && pad == 0) Wq = B * H * W, Hq = 1, Bq = 1, Ho = 1, Wo = Wq;
   UmmaParams p{};
-  pick_tile(Wo, Ho, KC, &p.TW, &p.TH);
+  pick_tile_k(Wo, Ho, KC, UK, &p.TW, &p.TH);
+  p.ksteps = p.TW * p.TH / UK;
   p.tiles_x = ceil_div(Wo, p.TW), p.tiles_y = ceil_div(Ho, p.TH), p.B = Bq;
   p.R = R, p.S = S, p.pad = pad;
   p.M = Cout, p.Cin = Cin;
   p.N = R * S * Cin;
-  p.block_n = pick_block_n(p.N, KC, p.N % 256 == 0 ? 256 : 192);
-  if (p.N % p.block_n) p.block_n = pick_block_n(p.N, KC, 256);
+  // N tile: a divisor of Cin (one tap, one box of block_n/KC channel groups) or a multiple of it (m whole taps, m boxes)
+  const int taps = R * S;
+  if (Cin >= 256) {
+    p.block_n = 256;
+    while (Cin % p.block_n) p.block_n -= KC;
+    p.gpt = p.block_n / KC, p.b_boxes = 1;
+  } else {
+    int best_m = 1;
+    double best_cost = 1e30;
+    for (int m = 1; m * Cin <= 256 && m <= 4; ++m) {
+      const double cost = (double)ceil_div(taps, m) * m * (m * Cin < 256 ? 1.15 : 1.0);  // narrow tiles are smem-bound
+      if (cost <= best_cost) best_cost = cost, best_m = m;
+    }
+    p.block_n = best_m * Cin, p.gpt = Cin / KC, p.b_boxes = best_m;
+  }
   p.n_tiles = ceil_div(p.N, p.block_n);
   p.m_tiles = ceil_div(Cout, 128);
   const long long total_q = (long long)p.tiles_x * p.tiles_y * Bq;
@@ -661,18 +688,21 @@ extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* d
   if (splits > total_q / 4) splits = total_q / 4;    // at least 4 chunks per split
   if (splits < 1) splits = 1;
   p.splits = (int)splits;
-  p.zero_smem = (p.TW * p.TH < KC) ? 1 : 0;
   p.ldo = p.N;
   CUtensorMap ta, tb, to;
   {
     long long od[2] = {p.N, Cout}, os[2] = {1, p.N};
     int obx[2] = {32, 128};
     if (int e = make_tmap(&to, SZN_F32, dw, 2, od, os, obx)) return e;
-    long long d[4] = {Cout, Wo, Ho, Bq}, s[4] = {1, ld_dy, (long long)Wo * ld_dy, (long long)Ho * Wo * ld_dy};
-    int bx[4] = {KC, p.TW, p.TH, 1};
-    if (int e = make_tmap(&ta, dtype, dy, 4, d, s, bx, true)) return e;
-    long long d2[4] = {Cin, Wq, Hq, Bq}, s2[4] = {1, Cin, (long long)Wq * Cin, (long long)Hq * Wq * Cin};
-    if (int e = make_tmap(&tb, dtype, x, 4, d2, s2, bx, true)) return e;
+    // 5-D views {KC channels, W, H, B, channel group}: one box fetches several 128-byte channel groups of a pixel patch
+    long long d[5] = {KC, Wo, Ho, Bq, Cout / KC};
+    long long s[5] = {1, ld_dy, (long long)Wo * ld_dy, (long long)Ho * Wo * ld_dy, KC};
+    int bx[5] = {KC, p.TW, p.TH, 1, 128 / KC};
+    if (int e = make_tmap(&ta, dtype, dy, 5, d, s, bx, true)) return e;
+    long long d2[5] = {KC, Wq, Hq, Bq, Cin / KC};
+    long long s2[5] = {1, Cin, (long long)Wq * Cin, (long long)Hq * Wq * Cin, KC};
+    int bx2[5] = {KC, p.TW, p.TH, 1, p.gpt};
+    if (int e = make_tmap(&tb, dtype, x, 5, d2, s2, bx2, true)) return e;
   }
   const long long grid = tiles * p.splits;
   return dtype == SZN_BF16 ? launch<__nv_bfloat16, 2>(ta, tb, to, p, grid, (cudaStream_t)stream)

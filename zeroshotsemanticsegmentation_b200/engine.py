@@ -9,7 +9,7 @@ Data layout in HBM
   * trunk activations: NHWC, element type = precision (``tf32``: fp32 rounded to TF32, ``bf16``);
   * packed weights ``[Cout][R*S][Cin]`` in the activation type, cached per parameter version;
   * head: ``s17`` = fp32 ``[B,hs,ws,Dp]`` holding ``score_fr`` (channels 0..D-1) and ``seenmask_score``
-    (channels D, D+1) from ONE GEMM, ``Dp`` = D+2 rounded up to 32;
+    (channels D, D+1) from ONE GEMM, ``Dp`` = D+2 rounded up to 64;
   * returned ``f`` (B,D,H,W) / ``s`` (B,2,H,W): NCHW fp32 contiguous, as the reference returns them.
 """
 from __future__ import annotations
@@ -123,7 +123,7 @@ class FCN32sFunction(torch.autograd.Function):
         B, _, H, W = x.shape
         P = dict(zip(PARAM_ORDER, params))
         D = P["score_fr.weight"].shape[0]
-        Dp = round_up(D + 2, 32)
+        Dp = round_up(D + 2, 64)
         pw = module._packed
 
         def packed(name, o_pad=None):
