@@ -36,6 +36,7 @@ struct UmmaParams {
   int Cin;      // MODE 2: channels per tap inside the N index
   int block_n, n_tiles, m_tiles, stages, splits, tmem_cols;
   int total_tiles;  // n_tiles * m_tiles (* splits): work items of the persistent tile loop
+  int nacc, acc_cols;  // accumulators per tile (K steps round-robin over them) and their TMEM column stride
   int gpt, b_boxes, ksteps;  // MODE 2: 128-byte column groups per B box, B boxes per stage, MMAs (K steps) per stage
   int dbg;  // timing experiments only (SZN_DBG / SZN_DBG_MODE env): bit0 skip A loads, bit1 skip B loads
   long long ldo;          // row stride of the output, elements (mask_ref shares it)
@@ -45,6 +46,8 @@ struct UmmaParams {
   int pix_per_image;      // rows per image for the scale lookup (H*W, or the original H*W when flattened)
   const void* mask_ref;   // dgrad: activation whose sign gates the gradient (ReLU backward) or null
   int relu, out_fp32;
+  int vec_ok;  // bias / scale rows are 16-byte aligned
+  long long* trace;  // debug (SZN_TRACE): clock64 stamps of CTA 0's roles, [role][tile][4]
 };
 
 template <typename T>
@@ -53,6 +56,25 @@ template <>
 __device__ __forceinline__ float load_as_float<float>(const float* p) { return *p; }
 template <>
 __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// out[j] = src[j] for j < nvalid (0 beyond); all loads are issued before any use
+template <int NV>
+__device__ __forceinline__ void load_row(const float* __restrict__ src, int cw, int nvalid, bool vec, float (&out)[NV]) {
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < NV / 4; ++j) {
+      if (4 * j < cw) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + j);
+        out[4 * j] = v.x, out[4 * j + 1] = v.y, out[4 * j + 2] = v.z, out[4 * j + 3] = v.w;
+      } else {
+        out[4 * j] = out[4 * j + 1] = out[4 * j + 2] = out[4 * j + 3] = 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) out[j] = (j < nvalid) ? __ldg(src + j) : 0.f;
+  }
+}
 
 struct TileCoord {
   int n0, b, x0, y0, m0, q_begin, n_iters;
@@ -185,6 +207,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       const uint32_t b_tx = (MODE == 2) ? (uint32_t)n_bbox * box_tx : (uint32_t)(block_n * 128);
+      const int tl = (tile - blockIdx.x) / gridDim.x;
+      if (p.trace && blockIdx.x == 0 && tl < 64) p.trace[(0 * 64 + tl) * 4 + 0] = clock64();
       for (int it = 0; it < t.n_iters; ++it) {
         mbar_wait(&empty[s], ph ^ 1u);
         uint8_t* a_dst = smem + s * stage_bytes;
@@ -230,9 +254,12 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const TileCoord t = decode_tile<MODE>(p, tile);
       if (t.n_iters == 0) continue;
       const uint32_t buf = local & 1u, aph = (local >> 1) & 1u;
+      const int tl = (int)local;
       ++local;
+      if (p.trace && blockIdx.x == 0 && tl < 64) p.trace[(1 * 64 + tl) * 4 + 0] = clock64();
       mbar_wait(&acce[buf], aph ^ 1u);  // the epilogue has drained this accumulator buffer
       tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && tl < 64) p.trace[(1 * 64 + tl) * 4 + 1] = clock64();
       const uint32_t dacc = tmem + buf * (uint32_t)p.tmem_cols;
       for (int it = 0; it < t.n_iters; ++it) {
         mbar_wait(&full[s], ph);
@@ -251,18 +278,23 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                       : umma_desc_sw128(a_addr + k * 32, 16, 1024);
           const uint64_t bdesc = B_MN ? umma_desc(b_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
                                       : umma_desc_sw128(b_addr + k * 32, 16, 1024);
-          tc_mma<TF32>(dacc, adesc, bdesc, idesc, (uint32_t)((it | k) != 0));
+          // consecutive MMAs into ONE accumulator serialise on its ~140-cycle read-modify-write latency (measured: 560
+          // cycles per 4-MMA stage whatever N is); narrow tiles therefore rotate over 2-4 accumulators that the epilogue adds
+          const int a = k & (p.nacc - 1);
+          tc_mma<TF32>(dacc + (uint32_t)(a * p.acc_cols), adesc, bdesc, idesc, (uint32_t)(it != 0 || k >= p.nacc));
         }
         tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
         if (++s == stages) s = 0, ph ^= 1u;
       }
       tc_commit(&accf[buf]);  // accumulator complete
+      if (p.trace && blockIdx.x == 0 && tl < 64) p.trace[(1 * 64 + tl) * 4 + 2] = clock64();
     }
   } else if (warp >= 2) {
     // =========================== epilogue ===========================
     constexpr int OUT_F32_ONLY = TF32 || MODE == 2;
     const bool f32_out = OUT_F32_ONLY || p.out_fp32;
     const int CW = f32_out ? 32 : 64;  // columns per 128-byte staging row
+    constexpr int CWMAX = OUT_F32_ONLY ? 32 : 64;
     const int q4 = warp & 3;           // TMEM lane quarter this warp may read
     const int row = q4 * 32 + lane;
     const bool issuer = (threadIdx.x == 64);
@@ -271,9 +303,12 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const TileCoord t = decode_tile<MODE>(p, tile);
       if (t.n_iters == 0) continue;
       const uint32_t buf = local & 1u, aph = (local >> 1) & 1u;
+      const int tl = (int)local;
       ++local;
+      if (p.trace && blockIdx.x == 0 && tl < 64 && issuer) p.trace[(2 * 64 + tl) * 4 + 0] = clock64();
       mbar_wait(&accf[buf], aph);
       tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && tl < 64 && issuer) p.trace[(2 * 64 + tl) * 4 + 1] = clock64();
       const uint32_t tbase = tmem + buf * (uint32_t)p.tmem_cols + ((uint32_t)(q4 * 32) << 16);
 
       bool ok = true;
@@ -292,20 +327,37 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int nb = t.n0 + c0;
         const bool last = (c == n_chunks - 1) || (nb + CW >= p.N);
         if (nb >= p.N) break;  // uniform: the whole chunk lies in the column padding
-        float f[64];
+        float f[CWMAX];
         {
           uint32_t v[32];
           tmem_ld32(tbase + (uint32_t)c0, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (!f32_out) {
-            tmem_ld32(tbase + (uint32_t)(c0 + 32), v);
+          for (int a = 1; a < p.nacc; ++a) {  // partial sums of the other accumulators
+            tmem_ld32(tbase + (uint32_t)(a * p.acc_cols + c0), v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[32 + j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+          }
+          if (CWMAX == 64) {
+            if (!f32_out) {
+              tmem_ld32(tbase + (uint32_t)(c0 + 32), v);
+              tmem_ld_wait();
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[(32 + j) % CWMAX] = f32_out ? 0.f : __uint_as_float(v[j]);
+            if (!f32_out) {
+              for (int a = 1; a < p.nacc; ++a) {
+                tmem_ld32(tbase + (uint32_t)(a * p.acc_cols + c0 + 32), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[(32 + j) % CWMAX] += __uint_as_float(v[j]);
+              }
+            }
           }
         }
+        if (p.trace && blockIdx.x == 0 && tl < 64 && issuer && c == 0) p.trace[(0 * 64 + tl) * 4 + 1] = clock64();  // after tmem ld
         if (last) {  // every TMEM read of this tile is done: hand the accumulator buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -313,20 +365,24 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         const int nvalid = (p.N - nb) < CW ? (p.N - nb) : CW;
         if (MODE != 2) {
+          // bias / Dropout2d scale rows: issue every load before the first use (32 dependent scalar loads per chunk
+          // cost ~3.7k cycles in the first trace), 16-byte vectors when the row is whole and aligned
+          const bool vec = (nvalid == CW) && p.vec_ok;
           if (p.bias) {
+            float bv[CWMAX];
+            load_row<CWMAX>(p.bias + nb, CW, nvalid, vec, bv);
 #pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (j < CW && j < nvalid) f[j] += __ldg(p.bias + nb + j);
+            for (int j = 0; j < CWMAX; ++j) f[j] += bv[j];
           }
           if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.f);
+            for (int j = 0; j < CWMAX; ++j) f[j] = fmaxf(f[j], 0.f);
           }
           if (p.scale) {
-            const float* sc = p.scale + (size_t)img * p.scale_ld + nb;
+            float sv[CWMAX];
+            load_row<CWMAX>(p.scale + (size_t)img * p.scale_ld + nb, CW, nvalid, vec, sv);
 #pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (j < CW && j < nvalid) f[j] *= __ldg(sc + j);
+            for (int j = 0; j < CWMAX; ++j) f[j] *= sv[j];
           }
           if (p.mask_ref && ok) {
             const T* ref = reinterpret_cast<const T*>(p.mask_ref) + orow * p.ldo + nb;
@@ -350,22 +406,26 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   for (int e = 0; e < 4; ++e) {
                     // bf16 > 0  <=>  sign bit clear and magnitude non-zero
                     const uint32_t lo = w[e] & 0xFFFFu, hi = w[e] >> 16;
-                    if ((lo & 0x8000u) || (lo & 0x7FFFu) == 0) f[8 * j + 2 * e] = 0.f;
-                    if ((hi & 0x8000u) || (hi & 0x7FFFu) == 0) f[8 * j + 2 * e + 1] = 0.f;
+                    if ((lo & 0x8000u) || (lo & 0x7FFFu) == 0) f[(8 * j + 2 * e) % CWMAX] = 0.f;
+                    if ((hi & 0x8000u) || (hi & 0x7FFFu) == 0) f[(8 * j + 2 * e + 1) % CWMAX] = 0.f;
                   }
                 }
               }
             } else {
-              for (int j = 0; j < nvalid; ++j)
-                if (!(load_as_float<T>(ref + j) > 0.f)) f[j] = 0.f;
+              // (compile-time indices only: a runtime index would push f[] into local memory)
+#pragma unroll
+              for (int j = 0; j < CWMAX; ++j)
+                if (j < nvalid && !(load_as_float<T>(ref + j) > 0.f)) f[j] = 0.f;
             }
           }
         }
         // ---- registers -> swizzled staging row -> TMA store ----
         uint8_t* sbuf = staging + (chunk_ctr & 1u) * STAGING_BYTES;
         ++chunk_ctr;
+        if (p.trace && blockIdx.x == 0 && tl < 64 && issuer && c == 0) p.trace[(0 * 64 + tl) * 4 + 2] = clock64();  // after math
         if (issuer) bulk_wait_read<1>();  // the store issued from this buffer two chunks ago has read it
         named_bar_sync(1, 128);
+        if (p.trace && blockIdx.x == 0 && tl < 64 && issuer && c == 0) p.trace[(0 * 64 + tl) * 4 + 3] = clock64();  // after wait+bar
         uint4 q[8];
         if (f32_out) {
           if (TF32 && MODE != 2 && !p.out_fp32) {
@@ -379,10 +439,10 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[(8 * j + 0) % CWMAX], f[(8 * j + 1) % CWMAX]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(f[(8 * j + 2) % CWMAX], f[(8 * j + 3) % CWMAX]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[(8 * j + 4) % CWMAX], f[(8 * j + 5) % CWMAX]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(f[(8 * j + 6) % CWMAX], f[(8 * j + 7) % CWMAX]);
             q[j].x = *reinterpret_cast<uint32_t*>(&h0);
             q[j].y = *reinterpret_cast<uint32_t*>(&h1);
             q[j].z = *reinterpret_cast<uint32_t*>(&h2);
@@ -395,11 +455,13 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < 8; ++j) srow[j ^ (row & 7)] = q[j];
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
+        if (p.trace && blockIdx.x == 0 && tl < 64 && issuer && c == 0) p.trace[(1 * 64 + tl) * 4 + 3] = clock64();  // after sts+fence+bar
         if (issuer && !(p.dbg & 4)) {
           if (MODE == 2) tma_reduce_add_2d(&tmO, sbuf, nb, t.m0);
           else tma_store_4d(&tmO, sbuf, nb, t.x0, t.y0, t.b);
           bulk_commit();
         }
+        if (p.trace && blockIdx.x == 0 && tl < 64 && issuer && c < 2) p.trace[(2 * 64 + tl) * 4 + 2 + c] = clock64();
       }
     }
     if (issuer) bulk_wait<0>();  // all stores have landed before the CTA (and its shared memory) goes away
@@ -508,8 +570,14 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
   int stages = (227 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
-  p.tmem_cols = tmem_cols_for(p.block_n);
+  p.acc_cols = tmem_cols_for(p.block_n);
+  p.nacc = p.acc_cols <= 64 ? 4 : p.acc_cols == 128 ? 2 : 1;
+  p.tmem_cols = p.acc_cols * p.nacc;  // per accumulator buffer; two buffers <= 512 columns
   p.total_tiles = (int)tiles;
+  {
+    const char* e = getenv("SZN_TRACE");
+    p.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr;
+  }
   {
     static int dbg = -1, dbg_mode = 0;
     if (dbg < 0) {
@@ -592,6 +660,7 @@ static int conv_gemm(int dtype, const void* x, long long ldx, const void* wt, co
   p.block_n = fill_sms(p.block_n, Cout, ngran, (long long)p.tiles_x * p.tiles_y * Bq);
   p.n_tiles = ceil_div(Cout, p.block_n);
   p.ldo = ldo, p.bias = bias, p.scale = scale, p.scale_ld = scale_ld, p.relu = relu, p.out_fp32 = out_fp32;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(scale)) & 15) == 0 && scale_ld % 4 == 0;
   p.mask_ref = mask_ref;
   CUtensorMap ta, tb, to;
   {
