@@ -24,7 +24,8 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libszn.so does not export %s" % n
     # every bound signature is declared in the header and vice versa
-    assert set(_lib.SIGNATURES) | {"szn_last_error", "szn_launch_count", "szn_abi_version"} == set(names)
+    assert set(_lib.SIGNATURES) | {"szn_last_error", "szn_launch_count", "szn_abi_version",
+                                   "szn_embed_argmax_scratch_floats"} == set(names)
 
 
 def test_no_cpu_fallback():

@@ -63,6 +63,8 @@ def load():
         fn.restype = I
     lib.szn_last_error.restype = ctypes.c_char_p
     lib.szn_launch_count.restype = LL
+    lib.szn_embed_argmax_scratch_floats.argtypes = [I, I]
+    lib.szn_embed_argmax_scratch_floats.restype = LL
     lib.szn_abi_version.restype = I
     _lib = lib
     return lib

@@ -699,10 +699,25 @@ extern "C" int szn_ce2d_bwd(const float* score, const long long* target, int n, 
   return check_launch("szn_ce2d_bwd");
 }
 
-// labels[n,h,w] (int64) = argmax_c cos(score[:, :, p], table[c]);  en_scratch: C floats
+namespace szn {
+int embed_argmax_tc(const float* score, const float* table, int n, int D, long long hw, int C, float* scratch,
+                    long long* labels, cudaStream_t st);
+}
+
+extern "C" long long szn_embed_argmax_scratch_floats(int C, int D) {
+  const long long Cpad = C <= 64 ? 64 : C <= 128 ? 128 : 256, Dpad = (D + 31) / 32 * 32;
+  const long long tc = 2 * Cpad * Dpad + Cpad;
+  return tc > C ? tc : C;
+}
+
+// labels[n,h,w] (int64) = argmax_c cos(score[:, :, p], table[c]);  en_scratch: szn_embed_argmax_scratch_floats(C, D) floats
 extern "C" int szn_embed_argmax(const float* score, const float* table, int n, int D, int h, int w, int C,
                                 float* en_scratch, long long* labels, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int rc = embed_argmax_tc(score, table, n, D, (long long)h * w, C, en_scratch, labels, st);
+    if (rc <= 0) return rc;  // launched on the tensor-core path (0) or failed (< 0); 1 = shape not covered, fall through
+  }
   table_norm_kernel<<<(C + 127) / 128, 128, 0, st>>>(table, C, D, en_scratch);
   if (int e = check_launch("szn_embed_argmax/norm")) return e;
   const long long hw = (long long)h * w;

@@ -100,41 +100,56 @@ __global__ void __launch_bounds__(128) conv1_1_fwd_kernel(const float* __restric
 }
 
 // conv1_1 weight gradient: dw[64][27] += sum_pixels dy[p][co] * x[p + tap - pad][ci]   (fp32 atomics)
+// Only output pixels whose 3x3 window touches the image contribute (x is zero elsewhere): with pad = 100 that is the
+// central (H+2) x (W+2) window, 52 % of the 710^2 map at 512^2.  A CTA stages 64 such pixels (dy rows and the 27 -> 4x8
+// padded taps); a thread owns one output channel and 7 taps, reading the taps as two 16-byte shared loads per pixel.
 template <typename T>
 __global__ void __launch_bounds__(256) conv1_1_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                             float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
-                                                            int pad, int nblocks_pix) {
+                                                            int pad, long long nblocks_pix) {
   __shared__ float sdy[64][65];
-  __shared__ float sx[64][28];
-  const int co = threadIdx.x & 63, kg = threadIdx.x >> 6;  // 4 groups of 7 taps*channels
+  __shared__ __align__(16) float sx[64][32];  // [pixel][4 groups x 8]: taps 7g..7g+6 of group g, slot 7 unused
+  const int co = threadIdx.x & 63, kg = threadIdx.x >> 6;
   float acc[7] = {0, 0, 0, 0, 0, 0, 0};
-  const long long total = (long long)B * Ho * Wo;
+  // contributing window of the output map
+  const int ylo = max(pad - 2, 0), xlo = max(pad - 2, 0);
+  const int yhi = min(pad + H - 1, Ho - 1), xhi = min(pad + W - 1, Wo - 1);
+  const int wy = yhi - ylo + 1, wx = xhi - xlo + 1;
+  const long long total = (long long)B * wy * wx;
   for (long long blk = blockIdx.x; blk < nblocks_pix; blk += gridDim.x) {
     const long long p0 = blk * 64;
-    // stage 64 pixels of dy (coalesced) and their 27 input taps
     for (int i = threadIdx.x; i < 64 * 64; i += 256) {
       const int px = i >> 6, c = i & 63;
-      const long long pix = p0 + px;
-      sdy[px][c] = pix < total ? as_float<T>(dy[pix * 64 + c]) : 0.f;
-    }
-    for (int i = threadIdx.x; i < 64 * 27; i += 256) {
-      const int px = i / 27, k = i - px * 27;
-      const long long pix = p0 + px;
+      const long long q = p0 + px;
       float v = 0.f;
-      if (pix < total) {
-        const int xo = (int)(pix % Wo), yo = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+      if (q < total) {
+        const int xo = xlo + (int)(q % wx), yo = ylo + (int)((q / wx) % wy), b = (int)(q / ((long long)wx * wy));
+        v = as_float<T>(dy[(((long long)b * Ho + yo) * Wo + xo) * 64 + c]);
+      }
+      sdy[px][c] = v;
+    }
+    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+      const int px = i >> 5, slot = i & 31;
+      const int g = slot >> 3, j = slot & 7, k = g * 7 + j;
+      const long long q = p0 + px;
+      float v = 0.f;
+      if (q < total && j < 7 && k < 27) {
+        const int xo = xlo + (int)(q % wx), yo = ylo + (int)((q / wx) % wy), b = (int)(q / ((long long)wx * wy));
         const int tap = k / 3, c = k - tap * 3;
         const int yi = yo + tap / 3 - pad, xi = xo + tap % 3 - pad;
         if (yi >= 0 && yi < H && xi >= 0 && xi < W) v = __ldg(x + (((long long)b * 3 + c) * H + yi) * W + xi);
       }
-      sx[px][k] = v;
+      sx[px][slot] = v;
     }
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 8
     for (int px = 0; px < 64; ++px) {
       const float d = sdy[px][co];
-#pragma unroll
-      for (int j = 0; j < 7; ++j) acc[j] = fmaf(d, sx[px][kg * 7 + j], acc[j]);
+      const float4 a0 = *reinterpret_cast<const float4*>(&sx[px][kg * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sx[px][kg * 8 + 4]);
+      acc[0] = fmaf(d, a0.x, acc[0]), acc[1] = fmaf(d, a0.y, acc[1]), acc[2] = fmaf(d, a0.z, acc[2]);
+      acc[3] = fmaf(d, a0.w, acc[3]), acc[4] = fmaf(d, a1.x, acc[4]), acc[5] = fmaf(d, a1.y, acc[5]);
+      acc[6] = fmaf(d, a1.z, acc[6]);
     }
     __syncthreads();
   }
@@ -192,75 +207,94 @@ __global__ void pool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, i
   }
 }
 
-// dY[b,y,x,c] = dP[b,y/2,x/2,c] if Y[b,y,x,c] is the FIRST maximum of its window (scan order, like ATen) and > 0 (ReLU)
+// dY[b,y,x,c] = dP[b,y/2,x/2,c] if Y[b,y,x,c] is the FIRST maximum of its window (scan order, like ATen) and > 0 (ReLU).
+// One thread = one 2x2 window x one 16-byte channel vector: every byte of Y, dP and dY moves exactly once.
 template <typename T>
-__global__ void pool_bwd_kernel(const T* __restrict__ yin, const T* __restrict__ dp, T* __restrict__ dy, int B, int H,
-                                int W, int C, int Ho, int Wo, int relu_gate) {
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const T* __restrict__ yin, const T* __restrict__ dp, T* __restrict__ dy,
+                                                       int B, int H, int W, int C, int Ho, int Wo, int relu_gate) {
   constexpr int VN = 16 / sizeof(T);
   const int cv = C / VN;
-  const long long total = (long long)B * H * W * cv;
+  const long long total = (long long)B * Ho * Wo * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % cv);
     long long r = i / cv;
-    const int x = (int)(r % W);
-    r /= W;
-    const int y = (int)(r % H);
-    const int b = (int)(r / H);
-    const int yo = y >> 1, xo = x >> 1;
-    const int me = (y & 1) * 2 + (x & 1);
-    float val[4][VN];
+    const int xo = (int)(r % Wo);
+    r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    uint4 u[4];
     bool have[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int yy = 2 * yo + (q >> 1), xx = 2 * xo + (q & 1);
       have[q] = yy < H && xx < W;
-      if (have[q]) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(yin + (((long long)b * H + yy) * W + xx) * C) + c);
-        const T* e = reinterpret_cast<const T*>(&u);
-#pragma unroll
-        for (int j = 0; j < VN; ++j) val[q][j] = as_float<T>(e[j]);
-      }
+      u[q] = have[q] ? __ldcs(reinterpret_cast<const uint4*>(yin + (((long long)b * H + yy) * W + xx) * C) + c)
+                     : make_uint4(0, 0, 0, 0);
     }
-    const uint4 gu = __ldg(reinterpret_cast<const uint4*>(dp + (((long long)b * Ho + yo) * Wo + xo) * C) + c);
+    const uint4 gu = __ldcs(reinterpret_cast<const uint4*>(dp + (((long long)b * Ho + yo) * Wo + xo) * C) + c);
     const T* ge = reinterpret_cast<const T*>(&gu);
-    uint4 o;
-    T* oe = reinterpret_cast<T*>(&o);
+    uint4 o[4];
 #pragma unroll
     for (int j = 0; j < VN; ++j) {
-      float mine = 0.f;
-      bool win = true;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q == me) mine = val[q][j];
+      float best = -INFINITY;
+      int win = 0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        if (q == me || !have[q]) continue;
-        if (q < me ? (val[q][j] >= mine) : (val[q][j] > mine)) win = false;
+        const float v = as_float<T>(reinterpret_cast<const T*>(&u[q])[j]);
+        if (have[q] && v > best) best = v, win = q;  // strict >: the first maximum in scan order keeps the gradient
       }
-      if (relu_gate && !(mine > 0.f)) win = false;
-      oe[j] = win ? ge[j] : from_float<T>(0.f);
+      const bool pass = !relu_gate || best > 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) reinterpret_cast<T*>(&o[q])[j] = (pass && q == win) ? ge[j] : from_float<T>(0.f);
     }
-    reinterpret_cast<uint4*>(dy + (((long long)b * H + y) * W + x) * C)[c] = o;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yy = 2 * yo + (q >> 1), xx = 2 * xo + (q & 1);
+      if (have[q]) __stcs(reinterpret_cast<uint4*>(dy + (((long long)b * H + yy) * W + xx) * C) + c, o[q]);
+    }
   }
 }
 
-// db[c] += sum over rows of dy[row][c]   (dy row stride ld)
+// db[c] += sum over rows of dy[row][c]   (dy row stride ld).  HBM-bound single pass: a thread owns one 16-byte channel
+// vector and walks rows with a block-wide stride, 4 loads in flight; partial sums meet in shared memory, one atomic per
+// (block, channel).
 template <typename T>
 __global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ dy, float* __restrict__ db, long long rows,
                                                         int C, long long ld, long long rows_per_block) {
-  __shared__ float red[4][64];
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  constexpr int VN = 16 / sizeof(T);
+  __shared__ float red[256 * VN];
+  const int cv = (C + VN - 1) / VN;          // channel vectors per row (C % VN == 0 is checked by the host)
+  const int lanes = cv < 256 ? cv : 256;      // threads along the channel axis
+  const int rstep = 256 / lanes;              // rows handled concurrently by the block
+  const int tc = threadIdx.x % lanes, tr = threadIdx.x / lanes;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
-  for (int cb = 0; cb < C; cb += 64) {
-    const int c = cb + tx;
-    float acc = 0.f;
-    if (c < C)
-      for (long long r = r0 + ty; r < r1; r += 4) acc += as_float<T>(dy[r * ld + c]);
-    red[ty][tx] = acc;
+  for (int c0 = 0; c0 < cv; c0 += lanes) {
+    const int c = c0 + tc;
+    float acc[VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) acc[j] = 0.f;
+    if (c < cv && tr < rstep) {
+#pragma unroll 4
+      for (long long r = r0 + tr; r < r1; r += rstep) {
+        const uint4 u = __ldcs(reinterpret_cast<const uint4*>(dy + r * ld) + c);
+        const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) acc[j] += as_float<T>(e[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VN; ++j) red[threadIdx.x * VN + j] = acc[j];
     __syncthreads();
-    if (ty == 0 && c < C) atomicAdd(db + c, red[0][tx] + red[1][tx] + red[2][tx] + red[3][tx]);
+    if (tr == 0 && c < cv) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        float t = 0.f;
+        for (int k = 0; k < rstep; ++k) t += red[(k * lanes + tc) * VN + j];
+        if (c * VN + j < C) atomicAdd(db + c * VN + j, t);
+      }
+    }
     __syncthreads();
   }
 }
@@ -404,9 +438,11 @@ extern "C" int szn_conv1_1_fwd(int dtype, const float* x, const float* w_oihw, c
 extern "C" int szn_conv1_1_wgrad(int dtype, const float* x, const void* dy, float* dw_oihw, int B, int H, int W, int pad,
                                  void* stream) {
   const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
-  const long long total = (long long)B * Ho * Wo;
-  const int nblk = (int)((total + 63) / 64);
-  const int grid = nblk < 148 * 4 ? nblk : 148 * 4;
+  const int wy = (pad + H - 1 < Ho - 1 ? pad + H - 1 : Ho - 1) - (pad - 2 > 0 ? pad - 2 : 0) + 1;
+  const int wx = (pad + W - 1 < Wo - 1 ? pad + W - 1 : Wo - 1) - (pad - 2 > 0 ? pad - 2 : 0) + 1;
+  const long long total = (long long)B * wy * wx;  // output pixels whose window touches the image
+  const long long nblk = (total + 63) / 64;
+  const int grid = (int)(nblk < 148 * 8 ? nblk : 148 * 8);
   DISPATCH_T(dtype, (conv1_1_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const T*)dy, dw_oihw, B, H, W, Ho, Wo, pad, nblk)));
   return check_launch("szn_conv1_1_wgrad");
 }
@@ -425,12 +461,15 @@ extern "C" int szn_pool_bwd(int dtype, const void* y, const void* dp, void* dy, 
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int vn = dtype == SZN_BF16 ? 8 : 4;
   if (C % vn) return set_error(SZN_ERR_ARG, "szn_pool_bwd: C must be a multiple of 16 bytes");
-  const long long total = (long long)B * H * W * (C / vn);
+  const long long total = (long long)B * Ho * Wo * (C / vn);
   DISPATCH_T(dtype, (pool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)y, (const T*)dp, (T*)dy, B, H, W, C, Ho, Wo, relu_gate)));
   return check_launch("szn_pool_bwd");
 }
 
 extern "C" int szn_bias_grad(int dtype, const void* dy, float* db, long long rows, int C, long long ld, void* stream) {
+  const int vn = dtype == SZN_BF16 ? 8 : 4;
+  if (C % vn || ld % vn || (reinterpret_cast<uintptr_t>(dy) & 15))
+    return set_error(SZN_ERR_ARG, "szn_bias_grad: C, ld and dy must be 16-byte aligned");
   long long rpb = (rows + 148 * 8 - 1) / (148 * 8);
   if (rpb < 64) rpb = 64;
   const unsigned grid = (unsigned)((rows + rpb - 1) / rpb);

@@ -128,7 +128,7 @@ def _labels_device(score, embed_arr):
     C, D = tb.shape
     if D != c:
         raise ValueError("embedding width %d does not match score channels %d" % (D, c))
-    en = torch.empty(C, device=score.device, dtype=torch.float32)
+    en = torch.empty(int(_lib.load().szn_embed_argmax_scratch_floats(C, D)), device=score.device, dtype=torch.float32)
     out = torch.empty((n, h, w), device=score.device, dtype=torch.int64)
     call("szn_embed_argmax", ptr(sc), ptr(tb), n, c, h, w, C, ptr(en), ptr(out), _lib.stream())
     return out
