@@ -15,6 +15,29 @@ __device__ __forceinline__ __nv_bfloat16 hfrom_float<__nv_bfloat16>(float f) { r
 
 constexpr int UPK = 64, UPS = 32, UPCROP = 19;
 
+template <int VEC>
+struct PixVec {
+  float v[VEC];
+};
+template <int VEC>
+__device__ __forceinline__ PixVec<VEC> ld_pix(const float* p) {
+  PixVec<VEC> r;
+  if (VEC == 4) {
+    const float4 f = __ldcs(reinterpret_cast<const float4*>(p));
+    r.v[0] = f.x, r.v[1 % VEC] = f.y, r.v[2 % VEC] = f.z, r.v[3 % VEC] = f.w;
+  } else {
+    r.v[0] = __ldcs(p);
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void st_pix(float* p, const PixVec<VEC>& r) {
+  if (VEC == 4) __stcs(reinterpret_cast<float4*>(p), make_float4(r.v[0], r.v[1 % VEC], r.v[2 % VEC], r.v[3 % VEC]));
+  else __stcs(p, r.v[0]);
+}
+
+
+
 // 1-D tent of get_upsampling_weight (models.py:11-19): k = 64 -> factor 32, centre 31.5
 __device__ __forceinline__ float tent(int k) { return 1.f - fabsf((float)k - 31.5f) * (1.f / 32.f); }
 
@@ -81,21 +104,22 @@ __global__ void __launch_bounds__(128) upsample_fwd_kernel(const float* __restri
 // HBM-bound on the read of g.  One CTA per (b, d) plane streams its H rows ONCE (coalesced, 8 rows in flight per
 // thread): a row feeds source row iy1 with weight f(ky) and iy1-1 with f(ky+32); when a 32-row group ends, the finished
 // column sums are folded along x by 8 threads per ix (64 taps each).
-template <typename T>
-__global__ void __launch_bounds__(512) upsample_bwd_kernel(const float* __restrict__ g, T* __restrict__ ds, int B, int D,
+// VEC = 4: a thread owns 4 adjacent columns and reads 16 bytes per row (W % 4 == 0); VEC = 1: any W.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ g, T* __restrict__ ds, int B, int D,
                                                            int H, int W, int hs, int ws, int ld, int coff) {
   extern __shared__ float col[];  // [W]
   const int plane = blockIdx.x;
   const int b = plane / D, d = plane - b * D;
   const float* gp = g + (long long)plane * H * W;
-  constexpr int NC = 2;  // columns per thread (W <= 1024)
-  float carry[NC], accA[NC], accB[NC];
+  const int X0 = threadIdx.x * VEC;  // W <= 256 * VEC
+  const bool live = X0 < W;
+  float carry[VEC], accA[VEC], accB[VEC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) carry[c] = accA[c] = accB[c] = 0.f;
+  for (int c = 0; c < VEC; ++c) carry[c] = accA[c] = accB[c] = 0.f;
   const int n_groups = (H + UPCROP + 31) >> 5;  // groups of rows with the same iy1 = (Y + 19) >> 5
   for (int k = 0; k <= n_groups; ++k) {
-    // rows of group k: u = Y + 19 in [32k, 32k + 31]
-    if (k < n_groups) {
+    if (k < n_groups && live) {  // rows of group k: u = Y + 19 in [32k, 32k + 31]
       int y0 = 32 * k - UPCROP, y1 = y0 + 32;
       if (y0 < 0) y0 = 0;
       if (y1 > H) y1 = H;
@@ -103,28 +127,24 @@ __global__ void __launch_bounds__(512) upsample_bwd_kernel(const float* __restri
       for (int Y = y0; Y < y1; ++Y) {
         const int ky = (Y + UPCROP) & 31;
         const float fy1 = tent(ky), fy0 = tent(ky + 32);
+        const PixVec<VEC> v = ld_pix<VEC>(gp + (long long)Y * W + X0);
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const int X = threadIdx.x + c * 512;
-          if (X < W) {
-            const float v = __ldcs(gp + (long long)Y * W + X);
-            accA[c] = fmaf(v, fy1, accA[c]);
-            accB[c] = fmaf(v, fy0, accB[c]);
-          }
+        for (int c = 0; c < VEC; ++c) {
+          accA[c] = fmaf(v.v[c], fy1, accA[c]);
+          accB[c] = fmaf(v.v[c], fy0, accB[c]);
         }
       }
     }
     // source row iy = k - 1 is complete: carry (its f(ky) part from group k-1) + accB (its f(ky+32) part from group k)
     const int iy = k - 1;
     if (iy >= 0 && iy < hs) {
+      if (live) {
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const int X = threadIdx.x + c * 512;
-        if (X < W) col[X] = carry[c] + accB[c];
+        for (int c = 0; c < VEC; ++c) col[X0 + c] = carry[c] + accB[c];
       }
       __syncthreads();
-      const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;  // 64 groups of 8 threads
-      for (int ix0 = 0; ix0 < ws; ix0 += 64) {  // warp-uniform trip count: every lane takes part in the shuffles
+      const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7, ngrp = blockDim.x >> 3;  // groups of 8 threads
+      for (int ix0 = 0; ix0 < ws; ix0 += ngrp) {  // warp-uniform trip count: every lane takes part in the shuffles
         const int ix = ix0 + grp;
         float acc = 0.f;
         if (ix < ws) {
@@ -141,7 +161,7 @@ __global__ void __launch_bounds__(512) upsample_bwd_kernel(const float* __restri
       __syncthreads();
     }
 #pragma unroll
-    for (int c = 0; c < NC; ++c) carry[c] = accA[c], accA[c] = 0.f, accB[c] = 0.f;
+    for (int c = 0; c < VEC; ++c) carry[c] = accA[c], accA[c] = 0.f, accB[c] = 0.f;
   }
 }
 
@@ -259,31 +279,10 @@ __device__ __forceinline__ void block_accumulate(double a, double b, double* acc
   }
 }
 
-template <int VEC>
-struct PixVec {
-  float v[VEC];
-};
-template <int VEC>
-__device__ __forceinline__ PixVec<VEC> ld_pix(const float* p) {
-  PixVec<VEC> r;
-  if (VEC == 4) {
-    const float4 f = __ldcs(reinterpret_cast<const float4*>(p));
-    r.v[0] = f.x, r.v[1 % VEC] = f.y, r.v[2 % VEC] = f.z, r.v[3 % VEC] = f.w;
-  } else {
-    r.v[0] = __ldcs(p);
-  }
-  return r;
-}
-template <int VEC>
-__device__ __forceinline__ void st_pix(float* p, const PixVec<VEC>& r) {
-  if (VEC == 4) __stcs(reinterpret_cast<float4*>(p), make_float4(r.v[0], r.v[1 % VEC], r.v[2 % VEC], r.v[3 % VEC]));
-  else __stcs(p, r.v[0]);
-}
-
 // One thread = VEC consecutive pixels of one image (VEC = 4: 16-byte loads of every channel plane, fully coalesced),
 // channel loop unrolled 4x so 4-8 independent 16-byte loads per thread are in flight: HBM-bound, one pass over score.
-template <int KIND, int VEC>
-__global__ void __launch_bounds__(256) embed_loss_fwd_kernel(const float* __restrict__ score, const long long* __restrict__ target,
+template <int KIND, int VEC, bool HAS_TE>
+__global__ void __launch_bounds__(256, 3) embed_loss_fwd_kernel(const float* __restrict__ score, const long long* __restrict__ target,
                                                              const float* __restrict__ te, const float* __restrict__ table,
                                                              int n, int c, long long hw, float* __restrict__ stats,
                                                              double* __restrict__ accum) {
@@ -299,18 +298,18 @@ __global__ void __launch_bounds__(256) embed_loss_fwd_kernel(const float* __rest
     for (int j = 0; j < VEC; ++j) t[j] = target[pix + j], any |= t[j] >= 0;
     if (any) {
       const float* sp = score + b * c * hw + p;
-      const float* ep = te ? te + b * c * hw + p : nullptr;
+      const float* ep = HAS_TE ? te + b * c * hw + p : nullptr;
       const float* tp[VEC];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) tp[j] = table ? table + (t[j] >= 0 ? t[j] : 0) * c : nullptr;
+      for (int j = 0; j < VEC; ++j) tp[j] = HAS_TE ? nullptr : table + (t[j] >= 0 ? t[j] : 0) * c;
       float ss[VEC], se[VEC], ee[VEC], sq[VEC];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) ss[j] = se[j] = ee[j] = sq[j] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
       for (int d = 0; d < c; ++d) {
         const PixVec<VEC> sv = ld_pix<VEC>(sp + d * hw);
         PixVec<VEC> ev;
-        if (ep) {
+        if (HAS_TE) {
           ev = ld_pix<VEC>(ep + d * hw);
         } else {
 #pragma unroll
@@ -347,8 +346,8 @@ __global__ void __launch_bounds__(256) embed_loss_fwd_kernel(const float* __rest
   block_accumulate(part, cnt, accum);
 }
 
-template <int KIND, int VEC>
-__global__ void __launch_bounds__(256) embed_loss_bwd_kernel(const float* __restrict__ score, const long long* __restrict__ target,
+template <int KIND, int VEC, bool HAS_TE>
+__global__ void __launch_bounds__(256, 3) embed_loss_bwd_kernel(const float* __restrict__ score, const long long* __restrict__ target,
                                                              const float* __restrict__ te, const float* __restrict__ table,
                                                              int n, int c, long long hw, const float* __restrict__ stats,
                                                              const double* __restrict__ accum, const float* __restrict__ gout,
@@ -372,12 +371,12 @@ __global__ void __launch_bounds__(256) embed_loss_bwd_kernel(const float* __rest
   }
   const float gs = gout[0] / (float)accum[1];
   const float* sp = score + b * c * hw + p;
-  const float* ep = te ? te + b * c * hw + p : nullptr;
+  const float* ep = HAS_TE ? te + b * c * hw + p : nullptr;
   const float* tp[VEC];
   float inv_s[VEC], inv_e[VEC], cs[VEC], live[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
-    tp[j] = table ? table + (t[j] >= 0 ? t[j] : 0) * c : nullptr;
+    tp[j] = HAS_TE ? nullptr : table + (t[j] >= 0 ? t[j] : 0) * c;
     live[j] = t[j] >= 0 ? 1.f : 0.f;
     inv_s[j] = inv_e[j] = cs[j] = 0.f;
     if (KIND == 0 && t[j] >= 0) {
@@ -385,11 +384,11 @@ __global__ void __launch_bounds__(256) embed_loss_bwd_kernel(const float* __rest
       inv_s[j] = st[0], inv_e[j] = st[1], cs[j] = st[2];
     }
   }
-#pragma unroll 4
+#pragma unroll 8
   for (int d = 0; d < c; ++d) {
     const PixVec<VEC> sv = ld_pix<VEC>(sp + d * hw);
     PixVec<VEC> ev, gv;
-    if (ep) {
+    if (HAS_TE) {
       ev = ld_pix<VEC>(ep + d * hw);
     } else {
 #pragma unroll
@@ -605,11 +604,17 @@ extern "C" int szn_upsample32_crop_bwd(int dtype, const float* g, void* ds, int 
                                        int ld, int coff, void* stream) {
   const unsigned grid = (unsigned)((long long)B * D);
   const size_t smem = (size_t)W * sizeof(float);
-  if (W > 1024) return set_error(SZN_ERR_UNSUPPORTED, "szn_upsample32_crop_bwd: W too large");
-  if (dtype == SZN_BF16)
-    upsample_bwd_kernel<__nv_bfloat16><<<grid, 512, smem, (cudaStream_t)stream>>>(g, (__nv_bfloat16*)ds, B, D, H, W, hs, ws, ld, coff);
-  else
-    upsample_bwd_kernel<float><<<grid, 512, smem, (cudaStream_t)stream>>>(g, (float*)ds, B, D, H, W, hs, ws, ld, coff);
+  const bool v4 = W % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+  if (W > (v4 ? 1024 : 256)) return set_error(SZN_ERR_UNSUPPORTED, "szn_upsample32_crop_bwd: W too large");
+  const int threads = v4 ? ((W / 4 + 31) / 32 * 32 < 64 ? 64 : (W / 4 + 31) / 32 * 32) : 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SZN_BF16) {
+    if (v4) upsample_bwd_kernel<__nv_bfloat16, 4><<<grid, threads, smem, st>>>(g, (__nv_bfloat16*)ds, B, D, H, W, hs, ws, ld, coff);
+    else upsample_bwd_kernel<__nv_bfloat16, 1><<<grid, threads, smem, st>>>(g, (__nv_bfloat16*)ds, B, D, H, W, hs, ws, ld, coff);
+  } else {
+    if (v4) upsample_bwd_kernel<float, 4><<<grid, threads, smem, st>>>(g, (float*)ds, B, D, H, W, hs, ws, ld, coff);
+    else upsample_bwd_kernel<float, 1><<<grid, threads, smem, st>>>(g, (float*)ds, B, D, H, W, hs, ws, ld, coff);
+  }
   return check_launch("szn_upsample32_crop_bwd");
 }
 
@@ -650,10 +655,13 @@ extern "C" int szn_embed_loss_fwd(int kind, const float* score, const long long*
   if (kind != 0 && kind != 1) return set_error(SZN_ERR_ARG, "szn_embed_loss_fwd: kind");
   const bool v4 = hw % 4 == 0 && ((reinterpret_cast<uintptr_t>(score) | reinterpret_cast<uintptr_t>(target_embed)) & 15) == 0;
   const unsigned grid = (unsigned)((total / (v4 ? 4 : 1) + 255) / 256);
-  if (kind == 0 && v4) embed_loss_fwd_kernel<0, 4><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum);
-  else if (kind == 0) embed_loss_fwd_kernel<0, 1><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum);
-  else if (v4) embed_loss_fwd_kernel<1, 4><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum);
-  else embed_loss_fwd_kernel<1, 1><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum);
+#define SZN_LOSS_FWD(K, V, TE) embed_loss_fwd_kernel<K, V, TE><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum)
+  const bool has_te = target_embed != nullptr;
+  if (kind == 0 && v4) { if (has_te) SZN_LOSS_FWD(0, 4, true); else SZN_LOSS_FWD(0, 4, false); }
+  else if (kind == 0) { if (has_te) SZN_LOSS_FWD(0, 1, true); else SZN_LOSS_FWD(0, 1, false); }
+  else if (v4) { if (has_te) SZN_LOSS_FWD(1, 4, true); else SZN_LOSS_FWD(1, 4, false); }
+  else { if (has_te) SZN_LOSS_FWD(1, 1, true); else SZN_LOSS_FWD(1, 1, false); }
+#undef SZN_LOSS_FWD
   if (int e = check_launch("szn_embed_loss_fwd")) return e;
   loss_finalize_kernel<<<1, 1, 0, st>>>(accum, kind, loss);
   return check_launch("szn_embed_loss_fwd/finalize");
@@ -673,10 +681,13 @@ extern "C" int szn_embed_loss_bwd(int kind, const float* score, const long long*
   const bool v4 = hw % 4 == 0 && ((reinterpret_cast<uintptr_t>(score) | reinterpret_cast<uintptr_t>(target_embed) |
                                    reinterpret_cast<uintptr_t>(dscore)) & 15) == 0;
   const unsigned grid = (unsigned)((total / (v4 ? 4 : 1) + 255) / 256);
-  if (kind == 0 && v4) embed_loss_bwd_kernel<0, 4><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum, grad_out, dscore);
-  else if (kind == 0) embed_loss_bwd_kernel<0, 1><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum, grad_out, dscore);
-  else if (v4) embed_loss_bwd_kernel<1, 4><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum, grad_out, dscore);
-  else embed_loss_bwd_kernel<1, 1><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum, grad_out, dscore);
+#define SZN_LOSS_BWD(K, V, TE) embed_loss_bwd_kernel<K, V, TE><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum, grad_out, dscore)
+  const bool has_te = target_embed != nullptr;
+  if (kind == 0 && v4) { if (has_te) SZN_LOSS_BWD(0, 4, true); else SZN_LOSS_BWD(0, 4, false); }
+  else if (kind == 0) { if (has_te) SZN_LOSS_BWD(0, 1, true); else SZN_LOSS_BWD(0, 1, false); }
+  else if (v4) { if (has_te) SZN_LOSS_BWD(1, 4, true); else SZN_LOSS_BWD(1, 4, false); }
+  else { if (has_te) SZN_LOSS_BWD(1, 1, true); else SZN_LOSS_BWD(1, 1, false); }
+#undef SZN_LOSS_BWD
   return check_launch("szn_embed_loss_bwd");
 }
 
