@@ -319,7 +319,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int y = t.y0 + ty, x = t.x0 + tx_;
         ok = row < rows_a && y < p.H && x < p.W;
         orow = ((size_t)t.b * p.H + y) * p.W + x;
-        img = (int)(orow / (size_t)p.pix_per_image);
+        img = ok ? (int)(orow / (size_t)p.pix_per_image) : 0;  // rows outside the image are clipped by the store
       }
       const int n_chunks = (block_n + CW - 1) / CW;
       for (int c = 0; c < n_chunks; ++c) {
