@@ -41,10 +41,12 @@ int szn_conv_fwd(int dtype, const void* x, const void* wt, const float* bias, vo
                  long long ldo, void* stream);
 /* dx[B,H,W,Cin] = conv_transpose(dy[B,Ho,Wo,Cout] (row stride ld_dy), w) * scale[b][ci] * (relu_ref[B,H,W,Cin] > 0)
  * wt_dgrad: the transposed, tap-flipped weights [Cin][R*S][Cout] written by szn_pack_weight_dgrad(mode 0); the data
- * gradient then runs as a forward conv of dy with padding R-1-pad on the same tensor-core path. */
+ * gradient then runs as a forward conv of dy with padding R-1-pad on the same tensor-core path.
+ * dx_col_sum (nullable, fp32 [Cin], zeroed by the caller): += column sums of the stored dx, i.e. the bias gradient of the
+ * layer that produced this conv's input, fused into the epilogue (one less pass over dx). */
 int szn_conv_dgrad(int dtype, const void* dy, const void* wt_dgrad, void* dx, int B, int H, int W, int Cin, int Cout,
                    int R, int S, int pad, const void* relu_ref, const float* scale, int scale_ld, long long ld_dy,
-                   void* stream);
+                   float* dx_col_sum, void* stream);
 /* dw[Cout][R*S*Cin] += sum_pixels dy (x) x   (fp32, split-K atomics: zero dw first) */
 int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int R,
                    int S, int pad, long long ld_dy, void* stream);
@@ -58,9 +60,10 @@ int szn_conv1_1_wgrad(int dtype, const float* x, const void* dy, float* dw_oihw,
 
 /* ---- MaxPool2d(2, stride=2, ceil_mode=True) (models.py:47,54,63,72,81) on NHWC ---- */
 int szn_pool_fwd(int dtype, const void* in, void* out, int B, int H, int W, int C, void* stream);
-/* dy = route dp to the first maximum of each window; relu_gate additionally zeroes positions where y <= 0 */
+/* dy = route dp to the first maximum of each window; relu_gate additionally zeroes positions where y <= 0.
+ * dy_col_sum (nullable, fp32 [C], zeroed by the caller): += per-channel sums of dy (the producer conv's bias gradient) */
 int szn_pool_bwd(int dtype, const void* y, const void* dp, void* dy, int B, int H, int W, int C, int relu_gate,
-                 void* stream);
+                 float* dy_col_sum, void* stream);
 
 /* db[C] += column sums of dy[rows][ld]  (bias gradients of every conv; zero db first) */
 int szn_bias_grad(int dtype, const void* dy, float* db, long long rows, int C, long long ld, void* stream);

@@ -152,14 +152,18 @@ def test_conv_dgrad(prec, case):
     (dx,) = torch.autograd.grad(y, x, dy)
     ref = dx * scale[:, :, None, None] * (ref_act > 0)
     out = torch.full((B, H, W, Cin), float("nan"), device=DEV, dtype=tdtype(prec))
+    colsum = torch.zeros(Cin, device=DEV)
     L = lib()
     L.call("szn_conv_dgrad", dcode(prec), dp(nhwc(dy, prec)), dp(pack_dgrad(w, prec)), dp(out), B, H, W,
-           Cin, Cout, k, k, pad, dp(nhwc(ref_act, prec)), dp(scale.to(DEV)), Cin, Cout, st())
+           Cin, Cout, k, k, pad, dp(nhwc(ref_act, prec)), dp(scale.to(DEV)), Cin, Cout, dp(colsum), st())
     torch.cuda.synchronize()
     got = from_nhwc(out)
     e = relerr(got, ref)
     print("conv_dgrad", prec, case, "relerr", e)
     assert e < (1e-3 if prec == "tf32" else 1e-2)
+    # fused bias gradient of the producer layer: column sums of exactly the values that were stored
+    want = got.sum(dim=(0, 2, 3))
+    assert relerr(colsum.cpu(), want) < 1e-5
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
@@ -176,7 +180,7 @@ def test_conv_dgrad_col2im(prec):
     L = lib()
     dcol = torch.full((B, Ho, Wo, k * k * Cin), float("nan"), device=DEV, dtype=tdtype(prec))
     L.call("szn_conv_dgrad", dcode(prec), dp(nhwc(dy, prec)), dp(pack_dgrad(w, prec, 1)), dp(dcol), B, Ho, Wo,
-           k * k * Cin, Cout, 1, 1, 0, None, None, 0, Cout, st())
+           k * k * Cin, Cout, 1, 1, 0, None, None, 0, Cout, None, st())
     out = torch.full((B, H, W, Cin), float("nan"), device=DEV, dtype=tdtype(prec))
     L.call("szn_col2im", dcode(prec), dp(dcol), dp(out), B, H, W, Cin, k, k, st())
     torch.cuda.synchronize()
@@ -252,9 +256,11 @@ def test_pool(prec, hw):
     (dy,) = torch.autograd.grad(p, y, dpool)
     ref = dy * (y.detach() > 0)
     dyo = torch.empty((B, H, W, C), device=DEV, dtype=tdtype(prec))
-    L.call("szn_pool_bwd", dcode(prec), dp(yd), dp(nhwc(dpool, prec)), dp(dyo), B, H, W, C, 1, st())
+    csum = torch.zeros(C, device=DEV)
+    L.call("szn_pool_bwd", dcode(prec), dp(yd), dp(nhwc(dpool, prec)), dp(dyo), B, H, W, C, 1, dp(csum), st())
     torch.cuda.synchronize()
     assert torch.equal(from_nhwc(dyo), ref)
+    assert relerr(csum.cpu(), ref.sum(dim=(0, 2, 3))) < 1e-5  # fused bias gradient of the conv in front of the pool
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])

@@ -52,11 +52,11 @@ for name, H, W, cin, cout, k, pad in layers:
     if name == "fc6":
         dcol = torch.empty(B, Ho, Wo, k * k * cin, device=dev, dtype=td)
         def dg():
-            _lib.call("szn_conv_dgrad", dt, dy.data_ptr(), wd.data_ptr(), dcol.data_ptr(), B, Ho, Wo, k * k * cin, cout, 1, 1, 0, None, None, 0, cout, st)
+            _lib.call("szn_conv_dgrad", dt, dy.data_ptr(), wd.data_ptr(), dcol.data_ptr(), B, Ho, Wo, k * k * cin, cout, 1, 1, 0, None, None, 0, cout, None, st)
             _lib.call("szn_col2im", dt, dcol.data_ptr(), dx.data_ptr(), B, H, W, cin, k, k, st)
         t_d = timeit(dg)
     else:
-        t_d = timeit(lambda: _lib.call("szn_conv_dgrad", dt, dy.data_ptr(), wd.data_ptr(), dx.data_ptr(), B, H, W, cin, cout, k, k, pad, x.data_ptr(), None, 0, cout, st))
+        t_d = timeit(lambda: _lib.call("szn_conv_dgrad", dt, dy.data_ptr(), wd.data_ptr(), dx.data_ptr(), B, H, W, cin, cout, k, k, pad, x.data_ptr(), None, 0, cout, None, st))
     t_w = timeit(lambda: _lib.call("szn_conv_wgrad", dt, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), B, H, W, cin, cout, k, k, pad, cout, st))
     tot["fwd"] += t_f; tot["dgrad"] += t_d; tot["wgrad"] += t_w
     print("%-8s %5d %5d %5d %5d | %9.3f ms %7.0f TF/s | %9.3f ms %7.0f TF/s | %9.3f ms %7.0f TF/s" %

@@ -15,12 +15,12 @@ I, LL, P, ULL = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_ulong
 # name -> argtypes (must mirror include/szn.h; tests/test_abi.py checks every symbol is exported)
 SIGNATURES = {
     "szn_conv_fwd": [I, P, P, P, P, I, I, I, I, I, I, I, I, I, P, I, I, LL, P],
-    "szn_conv_dgrad": [I, P, P, P, I, I, I, I, I, I, I, I, P, P, I, LL, P],
+    "szn_conv_dgrad": [I, P, P, P, I, I, I, I, I, I, I, I, P, P, I, LL, P, P],
     "szn_conv_wgrad": [I, P, P, P, I, I, I, I, I, I, I, I, LL, P],
     "szn_conv1_1_fwd": [I, P, P, P, P, I, I, I, I, P],
     "szn_conv1_1_wgrad": [I, P, P, P, I, I, I, I, P],
     "szn_pool_fwd": [I, P, P, I, I, I, I, P],
-    "szn_pool_bwd": [I, P, P, P, I, I, I, I, I, P],
+    "szn_pool_bwd": [I, P, P, P, I, I, I, I, I, P, P],
     "szn_bias_grad": [I, P, P, LL, I, LL, P],
     "szn_pack_weight": [I, P, P, I, I, I, I, I, P],
     "szn_pack_weight_dgrad": [I, P, P, I, I, I, I, I, I, P],

@@ -211,9 +211,16 @@ __global__ void pool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, i
 // One thread = one 2x2 window x one 16-byte channel vector: every byte of Y, dP and dY moves exactly once.
 template <typename T>
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const T* __restrict__ yin, const T* __restrict__ dp, T* __restrict__ dy,
-                                                       int B, int H, int W, int C, int Ho, int Wo, int relu_gate) {
+                                                       int B, int H, int W, int C, int Ho, int Wo, int relu_gate,
+                                                       float* __restrict__ col_sum) {
   constexpr int VN = 16 / sizeof(T);
   const int cv = C / VN;
+  // per-channel sums of dy (= of the routed dp values that pass the gate): the producer conv's bias gradient.
+  // 256 % cv == 0 is guaranteed by the host when col_sum is given, so a thread keeps ONE channel vector for the whole
+  // grid-stride loop and accumulates in registers; one shared-memory pass and C atomics per block at the end.
+  float csum[VN];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) csum[j] = 0.f;
   const long long total = (long long)B * Ho * Wo * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % cv);
@@ -246,11 +253,27 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const T* __restrict__ yin
       const bool pass = !relu_gate || best > 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) reinterpret_cast<T*>(&o[q])[j] = (pass && q == win) ? ge[j] : from_float<T>(0.f);
+      if (pass) csum[j] += as_float<T>(ge[j]);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int yy = 2 * yo + (q >> 1), xx = 2 * xo + (q & 1);
       if (have[q]) __stcs(reinterpret_cast<uint4*>(dy + (((long long)b * H + yy) * W + xx) * C) + c, o[q]);
+    }
+  }
+  if (col_sum) {
+    __shared__ float red[256 * VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) red[threadIdx.x * VN + j] = csum[j];
+    __syncthreads();
+    // threads t, t + cv, t + 2cv, ... hold the same channel vector (gridDim.x * 256 is a multiple of cv)
+    if ((int)threadIdx.x < cv) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        float t = 0.f;
+        for (int k = threadIdx.x; k < 256; k += cv) t += red[k * VN + j];
+        atomicAdd(col_sum + (((blockIdx.x * 256ll) + threadIdx.x) % cv) * VN + j, t);
+      }
     }
   }
 }
@@ -457,12 +480,13 @@ extern "C" int szn_pool_fwd(int dtype, const void* in, void* out, int B, int H, 
 }
 
 extern "C" int szn_pool_bwd(int dtype, const void* y, const void* dp, void* dy, int B, int H, int W, int C, int relu_gate,
-                            void* stream) {
+                            float* dy_col_sum, void* stream) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int vn = dtype == SZN_BF16 ? 8 : 4;
   if (C % vn) return set_error(SZN_ERR_ARG, "szn_pool_bwd: C must be a multiple of 16 bytes");
   const long long total = (long long)B * Ho * Wo * (C / vn);
-  DISPATCH_T(dtype, (pool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)y, (const T*)dp, (T*)dy, B, H, W, C, Ho, Wo, relu_gate)));
+  if (dy_col_sum && 256 % (C / vn)) return set_error(SZN_ERR_UNSUPPORTED, "szn_pool_bwd: fused channel sums need C/vector to divide 256");
+  DISPATCH_T(dtype, (pool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)y, (const T*)dp, (T*)dy, B, H, W, C, Ho, Wo, relu_gate, dy_col_sum)));
   return check_launch("szn_pool_bwd");
 }
 

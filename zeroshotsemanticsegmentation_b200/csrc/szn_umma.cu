@@ -47,6 +47,7 @@ struct UmmaParams {
   const void* mask_ref;   // dgrad: activation whose sign gates the gradient (ReLU backward) or null
   int relu, out_fp32;
   int vec_ok;  // bias / scale rows are 16-byte aligned
+  float* col_sum;  // dgrad: += column sums of the stored output (the producer layer's bias gradient) or null
   long long* trace;  // debug (SZN_TRACE): clock64 stamps of CTA 0's roles, [role][tile][4]
 };
 
@@ -447,6 +448,12 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             q[j].y = *reinterpret_cast<uint32_t*>(&h1);
             q[j].z = *reinterpret_cast<uint32_t*>(&h2);
             q[j].w = *reinterpret_cast<uint32_t*>(&h3);
+            if (MODE != 2 && p.col_sum) {  // the column sums must see exactly the values that are stored
+              f[(8 * j + 0) % CWMAX] = __low2float(h0), f[(8 * j + 1) % CWMAX] = __high2float(h0);
+              f[(8 * j + 2) % CWMAX] = __low2float(h1), f[(8 * j + 3) % CWMAX] = __high2float(h1);
+              f[(8 * j + 4) % CWMAX] = __low2float(h2), f[(8 * j + 5) % CWMAX] = __high2float(h2);
+              f[(8 * j + 6) % CWMAX] = __low2float(h3), f[(8 * j + 7) % CWMAX] = __high2float(h3);
+            }
           }
         }
         // SWIZZLE_128B: 16-byte chunk j of row r lives at chunk (j ^ (r & 7)); conflict-free for a warp's 32 rows
@@ -460,6 +467,29 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (MODE == 2) tma_reduce_add_2d(&tmO, sbuf, nb, t.m0);
           else tma_store_4d(&tmO, sbuf, nb, t.x0, t.y0, t.b);
           bulk_commit();
+        }
+        if (MODE != 2 && p.col_sum) {
+          // bias gradient of the layer that produced this dY: column sums of the stored tile.  Butterfly transpose-reduce:
+          // after 31 shuffles lane l holds the sum over the warp's 32 rows of column l; one RED per (warp, column).
+          const bool row_live = ok;
+#pragma unroll
+          for (int half = 0; half < CWMAX / 32; ++half) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = row_live ? f[half * 32 + j] : 0.f;
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) {
+              const bool up = (lane & sft) != 0;
+#pragma unroll
+              for (int i = 0; i < sft; ++i) {
+                const float send = up ? v[i] : v[i + sft];
+                const float keep = up ? v[i + sft] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+              }
+            }
+            const int col = nb + half * 32 + lane;
+            if (half * 32 < CW && col < p.N) atomicAdd(p.col_sum + col, v[0]);
+          }
         }
         if (p.trace && blockIdx.x == 0 && tl < 64 && issuer && c < 2) p.trace[(2 * 64 + tl) * 4 + 2 + c] = clock64();
       }
@@ -639,7 +669,7 @@ using namespace szn;
 // shared by the forward conv and the data gradient (which is a forward conv of dY with transposed, flipped weights)
 static int conv_gemm(int dtype, const void* x, long long ldx, const void* wt, const float* bias, void* y, int B, int H,
                      int W, int Cin, int Cout, int R, int S, int pad, int relu, const float* scale, int scale_ld,
-                     int out_fp32, long long ldo, const void* mask_ref, void* stream) {
+                     int out_fp32, long long ldo, const void* mask_ref, float* col_sum, void* stream) {
   const int KC = dtype == SZN_BF16 ? 64 : 32;
   if (Cin % KC && !(R == 1 && S == 1)) return set_error(SZN_ERR_ARG, "conv: channels per tap must be a multiple of 128 bytes");
   int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
@@ -662,6 +692,7 @@ static int conv_gemm(int dtype, const void* x, long long ldx, const void* wt, co
   p.ldo = ldo, p.bias = bias, p.scale = scale, p.scale_ld = scale_ld, p.relu = relu, p.out_fp32 = out_fp32;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(scale)) & 15) == 0 && scale_ld % 4 == 0;
   p.mask_ref = mask_ref;
+  p.col_sum = col_sum;
   CUtensorMap ta, tb, to;
   {
     long long od[4] = {Cout, Wo, Ho, Bq}, os[4] = {1, ldo, (long long)Wo * ldo, (long long)Ho * Wo * ldo};
@@ -684,7 +715,7 @@ extern "C" int szn_conv_fwd(int dtype, const void* x, const void* wt, const floa
                             int Cin, int Cout, int R, int S, int pad, int relu, const float* scale, int scale_ld,
                             int out_fp32, long long ldo, void* stream) {
   return conv_gemm(dtype, x, Cin, wt, bias, y, B, H, W, Cin, Cout, R, S, pad, relu, scale, scale_ld, out_fp32, ldo,
-                   nullptr, stream);
+                   nullptr, nullptr, stream);
 }
 
 // dx[B,H,W,Cin] (the conv input's gradient) from dy[B,Ho,Wo,Cout]:
@@ -695,10 +726,10 @@ extern "C" int szn_conv_fwd(int dtype, const void* x, const void* wt, const floa
 // `relu_ref` (same shape as dx) and per-(image, channel) multiplier `scale`.
 extern "C" int szn_conv_dgrad(int dtype, const void* dy, const void* wt_dgrad, void* dx, int B, int H, int W, int Cin,
                               int Cout, int R, int S, int pad, const void* relu_ref, const float* scale, int scale_ld,
-                              long long ld_dy, void* stream) {
+                              long long ld_dy, float* dx_col_sum, void* stream) {
   const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
   return conv_gemm(dtype, dy, ld_dy, wt_dgrad, nullptr, dx, B, Ho, Wo, Cout, Cin, R, S, R - 1 - pad, 0, scale, scale_ld,
-                   0, Cin, relu_ref, stream);
+                   0, Cin, relu_ref, dx_col_sum, stream);
 }
 
 // dw[Cout][R*S*Cin] (fp32, ACCUMULATED into: the caller zeroes it) from x[B,H,W,Cin] and dy[B,Ho,Wo,Cout]

@@ -276,16 +276,27 @@ class FCN32sFunction(torch.autograd.Function):
         if first_needed is None:
             return _finish(module, grads)
 
+        # Bias gradients are column sums of a layer's dY.  The kernel that WRITES that dY (the next layer's dgrad epilogue
+        # or the max-pool backward) accumulates them on the fly into `fused_db[layer]`, so dY is not read a second time.
+        fused_db = {}
+
+        def db_buffer(layer):
+            if not need[layer + ".bias"]:
+                return None
+            fused_db[layer] = zeros((P[layer + ".bias"].shape[0],))
+            return fused_db[layer]
+
         drop = sv["drop"]
         d7 = torch.empty((B, hs, ws, 4096), device=dev, dtype=tdtype)
         wf, ws_ = P["score_fr.weight"], P["seenmask_score.weight"]
         head_wd = pw.get(("head", "d", dt), (wf._version, ws_._version, wf.data_ptr()),
                          lambda: _pack_d(dt, tdtype, torch.cat([wf.detach(), ws_.detach()], 0).contiguous(), 0, Dp))
         call("szn_conv_dgrad", dt, ptr(ds17), ptr(head_wd), ptr(d7), B, hs, ws, 4096, Dp, 1, 1, 0,
-             ptr(sv["h7"]), ptr(drop[1]) if drop is not None else None, 4096, Dp, st)
+             ptr(sv["h7"]), ptr(drop[1]) if drop is not None else None, 4096, Dp, ptr(db_buffer("fc7")), st)
 
-        def conv_backward(name, x_act, dy, xh, xw, cin, cout, k, pad, want_dx, relu_ref, scale=None):
-            """wgrad + bias grad of one conv, then (optionally) its data gradient."""
+        def conv_backward(name, x_act, dy, xh, xw, cin, cout, k, pad, want_dx, relu_ref, scale=None, producer=None):
+            """wgrad + bias grad of one conv, then (optionally) its data gradient.  `producer`: the conv whose output
+            (after ReLU, no pool in between) is this conv's input, i.e. whose dY the dgrad epilogue writes."""
             ho, wo = xh + 2 * pad - k + 1, xw + 2 * pad - k + 1
             if need[name + ".weight"]:
                 dw = zeros((cout, k * k, cin))
@@ -294,9 +305,12 @@ class FCN32sFunction(torch.autograd.Function):
                 # same values, no unpack pass over 135 M gradients
                 grads[name + ".weight"] = dw.view(cout, k, k, cin).permute(0, 3, 1, 2)
             if need[name + ".bias"]:
-                db = zeros((cout,))
-                call("szn_bias_grad", dt, ptr(dy), ptr(db), B * ho * wo, cout, cout, st)
-                grads[name + ".bias"] = db
+                if name in fused_db:
+                    grads[name + ".bias"] = fused_db.pop(name)
+                else:
+                    db = zeros((cout,))
+                    call("szn_bias_grad", dt, ptr(dy), ptr(db), B * ho * wo, cout, cout, st)
+                    grads[name + ".bias"] = db
             if not want_dx:
                 return None
             dx = torch.empty((B, xh, xw, cin), device=dev, dtype=tdtype)
@@ -305,18 +319,19 @@ class FCN32sFunction(torch.autograd.Function):
                 # columns, which szn_col2im folds back; 98 full N tiles instead of 49 taps x a 512-wide N
                 dcol = torch.empty((B, ho, wo, k * k * cin), device=dev, dtype=tdtype)
                 call("szn_conv_dgrad", dt, ptr(dy), ptr(packed_d(name, 1)), ptr(dcol), B, ho, wo, k * k * cin, cout, 1, 1,
-                     0, None, None, 0, cout, st)
+                     0, None, None, 0, cout, None, st)
                 call("szn_col2im", dt, ptr(dcol), ptr(dx), B, xh, xw, cin, k, k, st)
                 return dx
             call("szn_conv_dgrad", dt, ptr(dy), ptr(packed_d(name)), ptr(dx), B, xh, xw, cin, cout, k, k, pad,
-                 ptr(relu_ref), ptr(scale), 4096 if scale is not None else 0, cout, st)
+                 ptr(relu_ref), ptr(scale), 4096 if scale is not None else 0, cout,
+                 ptr(db_buffer(producer)) if producer is not None else None, st)
             return dx
 
         n_convs = len(CONV_NAMES)
         # fc7 (index n_convs-1), fc6 (n_convs-2)
         h5, w5, _ = dims["pool5"]
         d6 = conv_backward("fc7", sv["h6"], d7, hs, ws, 4096, 4096, 1, 0, first_needed <= n_convs - 2, sv["h6"],
-                           drop[0] if drop is not None else None)
+                           drop[0] if drop is not None else None, producer="fc6")
         del d7
         if d6 is None:
             return _finish(module, grads)
@@ -332,7 +347,10 @@ class FCN32sFunction(torch.autograd.Function):
                 prev = rows[i - 1][0]
                 ph, pw_, pc = dims[prev]
                 dy = torch.empty((B, ph, pw_, pc), device=dev, dtype=tdtype)
-                call("szn_pool_bwd", dt, ptr(acts[prev]), ptr(g), ptr(dy), B, ph, pw_, pc, 1, st)
+                vec = 8 if tdtype == torch.bfloat16 else 4
+                fuse = 256 % (pc // vec) == 0
+                call("szn_pool_bwd", dt, ptr(acts[prev]), ptr(g), ptr(dy), B, ph, pw_, pc, 1,
+                     ptr(db_buffer(prev)) if fuse else None, st)
                 g = dy
             else:
                 name, cin, cout, k, pad = row
@@ -343,16 +361,19 @@ class FCN32sFunction(torch.autograd.Function):
                         call("szn_conv1_1_wgrad", dt, ptr(sv["x"]), ptr(g), ptr(dw), B, H, W, 100, st)
                         grads["conv1_1.weight"] = dw
                     if need["conv1_1.bias"]:
-                        db = zeros((64,))
-                        xh, xw, _ = dims["conv1_1"]
-                        call("szn_bias_grad", dt, ptr(g), ptr(db), B * xh * xw, 64, 64, st)
-                        grads["conv1_1.bias"] = db
+                        if "conv1_1" in fused_db:
+                            grads["conv1_1.bias"] = fused_db.pop("conv1_1")
+                        else:
+                            db = zeros((64,))
+                            xh, xw, _ = dims["conv1_1"]
+                            call("szn_bias_grad", dt, ptr(g), ptr(db), B * xh * xw, 64, 64, st)
+                            grads["conv1_1.bias"] = db
                     g = None
                 else:
                     prev = rows[i - 1][0]
                     xh, xw, _ = dims[prev]
                     prev_is_pool = len(rows[i - 1]) == 1
                     g = conv_backward(name, acts[prev], g, xh, xw, cin, cout, k, pad, first_needed < ci,
-                                      None if prev_is_pool else acts[prev])
+                                      None if prev_is_pool else acts[prev], producer=None if prev_is_pool else prev)
             i -= 1
         return _finish(module, grads)
