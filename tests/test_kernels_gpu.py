@@ -86,6 +86,8 @@ CONV_CASES = [
     (2, 9, 10, 64, 128, 7, 0),
     (2, 5, 7, 256, 320, 1, 0),
     (1, 23, 23, 128, 512, 3, 1),
+    (2, 33, 50, 64, 64, 3, 1),    # 3x3 halo-patch mode with the whole filter resident in shared memory (conv1_2-like)
+    (1, 48, 40, 256, 128, 3, 1),  # halo-patch mode, streamed weights, several tiles per CTA
 ]
 
 

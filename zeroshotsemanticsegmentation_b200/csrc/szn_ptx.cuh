@@ -85,6 +85,13 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// L2 prefetch of a box (no shared memory involved): turns the later load's HBM latency into an L2 hit
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"((uint64_t)m), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+
 // smem -> global tile stores through the tensor map (out-of-bounds rows / columns are clipped by the hardware)
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)m),

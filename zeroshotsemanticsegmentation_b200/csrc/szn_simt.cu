@@ -101,66 +101,86 @@ __global__ void __launch_bounds__(128) conv1_1_fwd_kernel(const float* __restric
 
 // conv1_1 weight gradient: dw[64][27] += sum_pixels dy[p][co] * x[p + tap - pad][ci]   (fp32 atomics)
 // Only output pixels whose 3x3 window touches the image contribute (x is zero elsewhere): with pad = 100 that is the
-// central (H+2) x (W+2) window, 52 % of the 710^2 map at 512^2.  A CTA stages 64 such pixels (dy rows and the 27 -> 4x8
-// padded taps); a thread owns one output channel and 7 taps, reading the taps as two 16-byte shared loads per pixel.
+// central (H+2) x (W+2) window, 52 % of the 710^2 map at 512^2.
+// Work item = 64 consecutive output pixels of one row.  576 threads = 64 output channels x 9 (input channel, filter row)
+// pairs; a thread slides a 3-wide window over the staged input row, so a pixel costs it one dY load (coalesced over the
+// channels), one shared-memory load and 3 FMAs for its three filter columns.  CTAs are persistent and keep their 3
+// partial sums in registers across all work items: 1728 atomics per CTA in total.
+constexpr int C11_SEG = 64;
 template <typename T>
-__global__ void __launch_bounds__(256) conv1_1_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+__global__ void __launch_bounds__(576) conv1_1_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                             float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
-                                                            int pad, long long nblocks_pix) {
-  __shared__ float sdy[64][65];
-  __shared__ __align__(16) float sx[64][32];  // [pixel][4 groups x 8]: taps 7g..7g+6 of group g, slot 7 unused
-  const int co = threadIdx.x & 63, kg = threadIdx.x >> 6;
-  float acc[7] = {0, 0, 0, 0, 0, 0, 0};
-  // contributing window of the output map
-  const int ylo = max(pad - 2, 0), xlo = max(pad - 2, 0);
-  const int yhi = min(pad + H - 1, Ho - 1), xhi = min(pad + W - 1, Wo - 1);
-  const int wy = yhi - ylo + 1, wx = xhi - xlo + 1;
-  const long long total = (long long)B * wy * wx;
-  for (long long blk = blockIdx.x; blk < nblocks_pix; blk += gridDim.x) {
-    const long long p0 = blk * 64;
-    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-      const int px = i >> 6, c = i & 63;
-      const long long q = p0 + px;
-      float v = 0.f;
-      if (q < total) {
-        const int xo = xlo + (int)(q % wx), yo = ylo + (int)((q / wx) % wy), b = (int)(q / ((long long)wx * wy));
-        v = as_float<T>(dy[(((long long)b * Ho + yo) * Wo + xo) * 64 + c]);
-      }
-      sdy[px][c] = v;
-    }
-    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
-      const int px = i >> 5, slot = i & 31;
-      const int g = slot >> 3, j = slot & 7, k = g * 7 + j;
-      const long long q = p0 + px;
-      float v = 0.f;
-      if (q < total && j < 7 && k < 27) {
-        const int xo = xlo + (int)(q % wx), yo = ylo + (int)((q / wx) % wy), b = (int)(q / ((long long)wx * wy));
-        const int tap = k / 3, c = k - tap * 3;
-        const int yi = yo + tap / 3 - pad, xi = xo + tap % 3 - pad;
-        if (yi >= 0 && yi < H && xi >= 0 && xi < W) v = __ldg(x + (((long long)b * 3 + c) * H + yi) * W + xi);
-      }
-      sx[px][slot] = v;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int px = 0; px < 64; ++px) {
-      const float d = sdy[px][co];
-      const float4 a0 = *reinterpret_cast<const float4*>(&sx[px][kg * 8]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&sx[px][kg * 8 + 4]);
-      acc[0] = fmaf(d, a0.x, acc[0]), acc[1] = fmaf(d, a0.y, acc[1]), acc[2] = fmaf(d, a0.z, acc[2]);
-      acc[3] = fmaf(d, a0.w, acc[3]), acc[4] = fmaf(d, a1.x, acc[4]), acc[5] = fmaf(d, a1.y, acc[5]);
-      acc[6] = fmaf(d, a1.z, acc[6]);
-    }
-    __syncthreads();
-  }
+                                                            int pad, int ylo, int xlo, int wy, int nseg) {
+  constexpr int VN = 16 / sizeof(T);                 // dY elements per 16-byte load
+  constexpr int NV = C11_SEG * 64 / VN;              // 16-byte vectors in one dY tile (64 px x 64 channels, contiguous)
+  constexpr int VPT = (NV + 575) / 576;              // vectors per thread
+  constexpr int XE = 9 * (C11_SEG + 2), XPT = (XE + 575) / 576;
+  __shared__ __align__(16) T sdy[2][C11_SEG * 64];
+  __shared__ float xs[2][9][C11_SEG + 2];  // [buffer][ci*3 + r][x]: the three input rows under this output row
+  const int co = threadIdx.x & 63, cr = threadIdx.x >> 6;  // cr = ci*3 + r
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  const long long items = (long long)B * wy * nseg;
+  uint4 rdy[VPT];
+  float rx[XPT];
+  // software pipeline: the global loads of item i+1 are in flight while item i is reduced out of shared memory
+  auto fetch = [&](long long it) {
+    const int seg = (int)(it % nseg);
+    const int yo = ylo + (int)((it / nseg) % wy);
+    const int b = (int)(it / ((long long)nseg * wy));
+    const int xo0 = xlo + seg * C11_SEG;
+    int npx = Wo - xo0;
+    if (npx > C11_SEG) npx = C11_SEG;
+    const uint4* src = reinterpret_cast<const uint4*>(dy + (((long long)b * Ho + yo) * Wo + xo0) * 64);
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    const int k = kg * 7 + j;
-    if (k < 27) {
-      const int tap = k / 3, c = k - tap * 3;
-      atomicAdd(dw + co * 27 + c * 9 + tap, acc[j]);  // OIHW
+    for (int v = 0; v < VPT; ++v) {
+      const int i = threadIdx.x + v * 576;
+      rdy[v] = (i < npx * 64 / VN) ? __ldcs(src + i) : make_uint4(0, 0, 0, 0);  // pixels past the row end count as 0
+    }
+#pragma unroll
+    for (int v = 0; v < XPT; ++v) {
+      const int i = threadIdx.x + v * 576;
+      float val = 0.f;
+      if (i < XE) {
+        const int row = i / (C11_SEG + 2), col = i - row * (C11_SEG + 2);
+        const int ci = row / 3, r = row - ci * 3;
+        const int yi = yo + r - pad, xi = xo0 - pad + col;
+        if (yi >= 0 && yi < H && xi >= 0 && xi < W) val = __ldg(x + (((long long)b * 3 + ci) * H + yi) * W + xi);
+      }
+      rx[v] = val;
+    }
+  };
+  int buf = 0;
+  if ((long long)blockIdx.x < items) fetch(blockIdx.x);
+  for (long long it = blockIdx.x; it < items; it += gridDim.x, buf ^= 1) {
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int i = threadIdx.x + v * 576;
+      if (i < NV) reinterpret_cast<uint4*>(sdy[buf])[i] = rdy[v];
+    }
+#pragma unroll
+    for (int v = 0; v < XPT; ++v) {
+      const int i = threadIdx.x + v * 576;
+      if (i < XE) (&xs[buf][0][0])[i] = rx[v];
+    }
+    __syncthreads();  // double-buffered: nobody still reads this buffer (its previous readers passed the last barrier)
+    if (it + gridDim.x < items) fetch(it + gridDim.x);
+    const T* d = sdy[buf] + co;
+    float w0 = xs[buf][cr][0], w1 = xs[buf][cr][1];
+#pragma unroll 16
+    for (int px = 0; px < C11_SEG; ++px) {
+      const float dv = as_float<T>(d[px * 64]);
+      const float w2 = xs[buf][cr][px + 2];
+      acc0 = fmaf(dv, w0, acc0);
+      acc1 = fmaf(dv, w1, acc1);
+      acc2 = fmaf(dv, w2, acc2);
+      w0 = w1, w1 = w2;
     }
   }
+  const int ci = cr / 3, r = cr - ci * 3;
+  float* o = dw + co * 27 + ci * 9 + r * 3;  // OIHW
+  atomicAdd(o, acc0);
+  atomicAdd(o + 1, acc1);
+  atomicAdd(o + 2, acc2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -461,12 +481,13 @@ extern "C" int szn_conv1_1_fwd(int dtype, const float* x, const float* w_oihw, c
 extern "C" int szn_conv1_1_wgrad(int dtype, const float* x, const void* dy, float* dw_oihw, int B, int H, int W, int pad,
                                  void* stream) {
   const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
-  const int wy = (pad + H - 1 < Ho - 1 ? pad + H - 1 : Ho - 1) - (pad - 2 > 0 ? pad - 2 : 0) + 1;
-  const int wx = (pad + W - 1 < Wo - 1 ? pad + W - 1 : Wo - 1) - (pad - 2 > 0 ? pad - 2 : 0) + 1;
-  const long long total = (long long)B * wy * wx;  // output pixels whose window touches the image
-  const long long nblk = (total + 63) / 64;
-  const int grid = (int)(nblk < 148 * 8 ? nblk : 148 * 8);
-  DISPATCH_T(dtype, (conv1_1_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const T*)dy, dw_oihw, B, H, W, Ho, Wo, pad, nblk)));
+  const int ylo = pad - 2 > 0 ? pad - 2 : 0, xlo = ylo;
+  const int yhi = pad + H - 1 < Ho - 1 ? pad + H - 1 : Ho - 1, xhi = pad + W - 1 < Wo - 1 ? pad + W - 1 : Wo - 1;
+  const int wy = yhi - ylo + 1, wx = xhi - xlo + 1;  // output pixels whose window touches the image
+  const int nseg = (wx + C11_SEG - 1) / C11_SEG;
+  const long long items = (long long)B * wy * nseg;
+  const int grid = (int)(items < 148 * 3 ? items : 148 * 3);
+  DISPATCH_T(dtype, (conv1_1_wgrad_kernel<T><<<grid, 576, 0, (cudaStream_t)stream>>>(x, (const T*)dy, dw_oihw, B, H, W, Ho, Wo, pad, ylo, xlo, wy, nseg)));
   return check_launch("szn_conv1_1_wgrad");
 }
 
