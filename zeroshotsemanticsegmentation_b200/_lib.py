@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libszn.so")
+LIB_PATH = os.environ.get("SZN_LIB") or os.path.join(_HERE, "libszn.so")  # SZN_LIB: A/B-test another build
 
 I, LL, P, ULL = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_ulonglong
 

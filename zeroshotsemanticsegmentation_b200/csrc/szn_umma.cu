@@ -36,6 +36,8 @@ struct UmmaParams {
   int Cin;      // MODE 2: channels per tap inside the N index
   int block_n, n_tiles, m_tiles, stages, splits, tmem_cols;
   int total_tiles;  // n_tiles * m_tiles (* splits): work items of the persistent tile loop
+  int mpair;  // MODE 2: 128-row output sub-tiles per work item (2: two accumulators share every B stage)
+  int nbuf;   // accumulator buffers in TMEM (2 unless one tile needs all 512 columns)
   int nacc, acc_cols;  // accumulators per tile (K steps round-robin over them) and their TMEM column stride
   int gpt, b_boxes, ksteps;  // MODE 2: 128-byte column groups per B box, B boxes per stage, MMAs (K steps) per stage
   int dbg;  // timing experiments only (SZN_DBG / SZN_DBG_MODE env): bit0 skip A loads, bit1 skip B loads
@@ -93,7 +95,7 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   if (MODE == 2) {
     const int m_tile = idx % p.m_tiles, split = idx / p.m_tiles;
-    t.m0 = m_tile * 128;
+    t.m0 = m_tile * 128 * p.mpair;
     const int total_q = tiles_per_img * p.B;
     const int per = (total_q + p.splits - 1) / p.splits;
     t.q_begin = split * per;
@@ -136,7 +138,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
   const int block_n = p.block_n;
-  const int stage_bytes = A_BYTES + block_n * 128;
+  const int mp = (MODE == 2) ? p.mpair : 1;
+  const int a_bytes = A_BYTES * mp;
+  const int stage_bytes = a_bytes + block_n * 128;
   const int stages = p.stages;
   uint8_t* staging = smem + stages * stage_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(staging + 2 * STAGING_BYTES);
@@ -164,7 +168,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tptr, (uint32_t)(2 * p.tmem_cols));
+    tmem_alloc(tptr, (uint32_t)(p.nbuf * p.tmem_cols));
     tmem_relinquish();
   }
   tc_fence_before();
@@ -182,7 +186,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // MODE 2 operands are fetched with 5-D boxes {KC channels, TW, TH, 1, G channel groups}: one box lands G column
     // groups (each rows_a x 128 B, back to back) instead of one 4 KB box per group -- the TMA unit pays a fixed cost per
     // box, and twelve small boxes per stage made the wgrad load-bound.
-    const uint32_t a_tx = (MODE == 2) ? (uint32_t)((128 / KC) * rows_a * 128) : (uint32_t)(rows_a * 128);
+    const uint32_t a_tx = (MODE == 2) ? (uint32_t)(mp * (128 / KC) * rows_a * 128) : (uint32_t)(rows_a * 128);
     const uint32_t box_tx = (uint32_t)(p.gpt * rows_a * 128);  // MODE 2: bytes of one B box
     int s = 0;
     uint32_t ph = 0;
@@ -213,7 +217,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int it = 0; it < t.n_iters; ++it) {
         mbar_wait(&empty[s], ph ^ 1u);
         uint8_t* a_dst = smem + s * stage_bytes;
-        uint8_t* b_dst = a_dst + A_BYTES;
+        uint8_t* b_dst = a_dst + a_bytes;
         const bool skip_a = (p.dbg & 1) && it >= stages, skip_b = (p.dbg & 2) && it >= stages;  // timing experiments
         const uint32_t tx = (skip_a ? 0u : a_tx) + (skip_b ? 0u : b_tx);
         if (tx) mbar_expect_tx(&full[s], tx);
@@ -254,7 +258,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<MODE>(p, tile);
       if (t.n_iters == 0) continue;
-      const uint32_t buf = local & 1u, aph = (local >> 1) & 1u;
+      const uint32_t buf = p.nbuf == 2 ? (local & 1u) : 0u, aph = p.nbuf == 2 ? ((local >> 1) & 1u) : (local & 1u);
       const int tl = (int)local;
       ++local;
       if (p.trace && blockIdx.x == 0 && tl < 64) p.trace[(1 * 64 + tl) * 4 + 0] = clock64();
@@ -266,7 +270,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-        const uint32_t b_addr = a_addr + A_BYTES;
+        const uint32_t b_addr = a_addr + a_bytes;
         // K-major: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzled row.
         // MN-major: 128 B-wide column groups LBO = rows_a*128 B apart (as the 5-D TMA box lays them down), K advances UK
         // rows of 128 B per MMA; the K rows come in groups SBO apart: 8 rows / 1024 B for 16-bit operands (SWIZZLE_128B),
@@ -274,15 +278,27 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         constexpr uint32_t MN_LAYOUT = TF32 ? 1u : 2u, MN_SBO = TF32 ? 512u : 1024u;
         const uint32_t lbo = (uint32_t)rows_a * 128u;
         const int ksteps = (MODE == 2) ? p.ksteps : 4;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t adesc = A_MN ? umma_desc(a_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
-                                      : umma_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t bdesc = B_MN ? umma_desc(b_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
-                                      : umma_desc_sw128(b_addr + k * 32, 16, 1024);
-          // consecutive MMAs into ONE accumulator serialise on its ~140-cycle read-modify-write latency (measured: 560
-          // cycles per 4-MMA stage whatever N is); narrow tiles therefore rotate over 2-4 accumulators that the epilogue adds
-          const int a = k & (p.nacc - 1);
-          tc_mma<TF32>(dacc + (uint32_t)(a * p.acc_cols), adesc, bdesc, idesc, (uint32_t)(it != 0 || k >= p.nacc));
+        if (MODE == 2 && mp == 2) {
+          // two 128-row sub-tiles share the B stage.  (A separate loop, not a predicated second MMA inside the common
+          // loop: a predicated-off UTCHMMA still cost the single-tile path 25 %.)
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = umma_desc(a_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT);
+            const uint64_t adesc2 = umma_desc(a_addr + (128 / KC) * lbo + k * UK * 128, lbo, MN_SBO, MN_LAYOUT);
+            const uint64_t bdesc = umma_desc(b_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT);
+            tc_mma<TF32>(dacc, adesc, bdesc, idesc, (uint32_t)((it | k) != 0));
+            tc_mma<TF32>(dacc + (uint32_t)p.acc_cols, adesc2, bdesc, idesc, (uint32_t)((it | k) != 0));
+          }
+        } else {
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = A_MN ? umma_desc(a_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
+                                        : umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_desc(b_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
+                                        : umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            // consecutive MMAs into ONE accumulator serialise on its ~140-cycle read-modify-write latency (measured: 560
+            // cycles per 4-MMA stage whatever N is); narrow tiles therefore rotate over 2-4 accumulators that the epilogue adds
+            const int a = k & (p.nacc - 1);
+            tc_mma<TF32>(dacc + (uint32_t)(a * p.acc_cols), adesc, bdesc, idesc, (uint32_t)(it != 0 || k >= p.nacc));
+          }
         }
         tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
         if (++s == stages) s = 0, ph ^= 1u;
@@ -303,7 +319,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<MODE>(p, tile);
       if (t.n_iters == 0) continue;
-      const uint32_t buf = local & 1u, aph = (local >> 1) & 1u;
+      const uint32_t buf = p.nbuf == 2 ? (local & 1u) : 0u, aph = p.nbuf == 2 ? ((local >> 1) & 1u) : (local & 1u);
       const int tl = (int)local;
       ++local;
       if (p.trace && blockIdx.x == 0 && tl < 64 && issuer) p.trace[(2 * 64 + tl) * 4 + 0] = clock64();
@@ -323,34 +339,36 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         img = ok ? (int)(orow / (size_t)p.pix_per_image) : 0;  // rows outside the image are clipped by the store
       }
       const int n_chunks = (block_n + CW - 1) / CW;
-      for (int c = 0; c < n_chunks; ++c) {
+      for (int hc = 0; hc < mp * n_chunks; ++hc) {
+        const int h = hc / n_chunks, c = hc - h * n_chunks;  // h: 128-row sub-tile (MODE 2 with mpair = 2)
+        const uint32_t tb = tbase + (uint32_t)(h * p.acc_cols);
         const int c0 = c * CW;
         const int nb = t.n0 + c0;
-        const bool last = (c == n_chunks - 1) || (nb + CW >= p.N);
-        if (nb >= p.N) break;  // uniform: the whole chunk lies in the column padding
+        const bool last = (h == mp - 1) && ((c == n_chunks - 1) || (nb + CW >= p.N));
+        if (nb >= p.N) continue;  // uniform: the whole chunk lies in the column padding
         float f[CWMAX];
         {
           uint32_t v[32];
-          tmem_ld32(tbase + (uint32_t)c0, v);
+          tmem_ld32(tb + (uint32_t)c0, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           for (int a = 1; a < p.nacc; ++a) {  // partial sums of the other accumulators
-            tmem_ld32(tbase + (uint32_t)(a * p.acc_cols + c0), v);
+            tmem_ld32(tb + (uint32_t)(a * p.acc_cols + c0), v);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
           }
           if (CWMAX == 64) {
             if (!f32_out) {
-              tmem_ld32(tbase + (uint32_t)(c0 + 32), v);
+              tmem_ld32(tb + (uint32_t)(c0 + 32), v);
               tmem_ld_wait();
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[(32 + j) % CWMAX] = f32_out ? 0.f : __uint_as_float(v[j]);
             if (!f32_out) {
               for (int a = 1; a < p.nacc; ++a) {
-                tmem_ld32(tbase + (uint32_t)(a * p.acc_cols + c0 + 32), v);
+                tmem_ld32(tb + (uint32_t)(a * p.acc_cols + c0 + 32), v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[(32 + j) % CWMAX] += __uint_as_float(v[j]);
@@ -464,7 +482,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         named_bar_sync(1, 128);
         if (p.trace && blockIdx.x == 0 && tl < 64 && issuer && c == 0) p.trace[(1 * 64 + tl) * 4 + 3] = clock64();  // after sts+fence+bar
         if (issuer && !(p.dbg & 4)) {
-          if (MODE == 2) tma_reduce_add_2d(&tmO, sbuf, nb, t.m0);
+          if (MODE == 2) tma_reduce_add_2d(&tmO, sbuf, nb, t.m0 + h * 128);
           else tma_store_4d(&tmO, sbuf, nb, t.x0, t.y0, t.b);
           bulk_commit();
         }
@@ -499,7 +517,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, (uint32_t)(2 * p.tmem_cols));
+  if (warp == 2) tmem_dealloc(tmem, (uint32_t)(p.nbuf * p.tmem_cols));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -595,14 +613,16 @@ static int num_sms() {
 template <typename T, int MODE>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, UmmaParams& p, long long tiles,
                   cudaStream_t st) {
-  const int stage_bytes = 128 * 128 + p.block_n * 128;
+  const int stage_bytes = 128 * 128 * (MODE == 2 && p.mpair == 2 ? 2 : 1) + p.block_n * 128;
   const int fixed = 2 * 128 * 128 /* epilogue staging */ + 1024 /* alignment */ + 256 /* barriers */;
   int stages = (227 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
   p.acc_cols = tmem_cols_for(p.block_n);
   p.nacc = p.acc_cols <= 64 ? 4 : p.acc_cols == 128 ? 2 : 1;
-  p.tmem_cols = p.acc_cols * p.nacc;  // per accumulator buffer; two buffers <= 512 columns
+  if (MODE != 2 || p.mpair < 1) p.mpair = 1;
+  p.tmem_cols = p.acc_cols * p.nacc * p.mpair;  // per accumulator buffer
+  p.nbuf = 2 * p.tmem_cols <= 512 ? 2 : 1;
   p.total_tiles = (int)tiles;
   {
     const char* e = getenv("SZN_TRACE");
@@ -781,7 +801,14 @@ extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* d
     p.block_n = best_m * Cin, p.gpt = Cin / KC, p.b_boxes = best_m;
   }
   p.n_tiles = ceil_div(p.N, p.block_n);
-  p.m_tiles = ceil_div(Cout, 128);
+  // two 128-row output sub-tiles per work item when Cout allows: they share every B (x) stage, so the bytes fetched per
+  // MMA cycle drop from 96 to 64 -- the wgrad streams both operands once and is bound by load latency x ring depth
+  {
+    static int no_pair = -1;
+    if (no_pair < 0) no_pair = getenv("SZN_NO_MPAIR") ? 1 : 0;
+    p.mpair = (!no_pair && Cout >= 256 && p.block_n == 256) ? 2 : 1;
+  }
+  p.m_tiles = ceil_div(Cout, 128 * p.mpair);
   const long long total_q = (long long)p.tiles_x * p.tiles_y * Bq;
   const long long tiles = (long long)p.n_tiles * p.m_tiles;
   long long splits = (2 * 148 + tiles - 1) / tiles;  // about two waves of CTAs
@@ -797,7 +824,7 @@ extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* d
     // 5-D views {KC channels, W, H, B, channel group}: one box fetches several 128-byte channel groups of a pixel patch
     long long d[5] = {KC, Wo, Ho, Bq, Cout / KC};
     long long s[5] = {1, ld_dy, (long long)Wo * ld_dy, (long long)Ho * Wo * ld_dy, KC};
-    int bx[5] = {KC, p.TW, p.TH, 1, 128 / KC};
+    int bx[5] = {KC, p.TW, p.TH, 1, (128 / KC) * p.mpair};
     if (int e = make_tmap(&ta, dtype, dy, 5, d, s, bx, true)) return e;
     long long d2[5] = {KC, Wq, Hq, Bq, Cin / KC};
     long long s2[5] = {1, Cin, (long long)Wq * Cin, (long long)Hq * Wq * Cin, KC};
