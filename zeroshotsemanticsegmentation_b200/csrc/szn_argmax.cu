@@ -115,6 +115,7 @@ embed_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_con
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer ----------------
     const uint32_t idesc = umma_idesc(2, 1, 0, 128, p.Cpad);  // tf32, A MN-major, B K-major
+    const uint32_t idesc2 = umma_idesc(2, 1, 0, 128, 2 * p.Cpad);
     int s = 0;
     uint32_t ph = 0, local = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -138,9 +139,11 @@ embed_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_con
           const uint64_t bh = umma_desc_sw128(b_hi + k * 32, 16, 1024);
           const uint64_t bl = umma_desc_sw128(b_lo + k * 32, 16, 1024);
           const uint32_t acc = (uint32_t)((kc | k) != 0);
-          tc_mma<true>(d0, ah, bh, idesc, acc);
-          tc_mma<true>(d0 + (uint32_t)p.acc_cols, al, bh, idesc, acc);
-          tc_mma<true>(d0 + 2u * (uint32_t)p.acc_cols, ah, bl, idesc, acc);
+          // B_hi and B_lo are stacked along N, so A_hi x [B_hi; B_lo] yields the hi*hi and hi*lo partial sums with ONE
+          // instruction (an N <= 256 MMA costs about the same ~130 cycles whatever N is); lo*hi is the second one.
+          tc_mma<true>(d0, ah, bh, idesc2, acc);                              // columns [0, 2*Cpad): hh | hl
+          tc_mma<true>(d0 + 2u * (uint32_t)p.acc_cols, al, bh, idesc, acc);  // columns [2*Cpad, 3*Cpad): lh
+          (void)bl;
         }
         tc_commit(&empty[s]);
         if (++s == stages) s = 0, ph ^= 1u;
