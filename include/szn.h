@@ -126,6 +126,12 @@ int szn_stitch_labels(const long long* lbl_seen, const long long* lbl_unseen, co
                       const long long* target, const long long* unseen, int n_unseen, int n, int h, int w,
                       long long* out, void* stream);
 
+/* ---- metrics (utils.py:104-154, called after every iteration: trainer_fcn.py:164,223,248) ----
+ * Confusion matrices of _fast_hist for target = 'all' (and 'seen' / 'unseen' when is_unseen[n_class] is given), built on
+ * the device-resident label maps.  hist: int64 [1 or 3][n_class][n_class], accumulated into (zero it first). */
+int szn_confusion_hist(const long long* label_true, const long long* label_pred, long long n, int n_class,
+                       const unsigned char* is_unseen, long long* hist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,3 +61,20 @@ def test_module_surface_matches_reference():
     m.copy_params_from_vgg16(vgg)
     assert torch.equal(m.conv3_2.weight, vgg.features[7].weight)
     assert torch.equal(m.fc6.weight.view(4096, -1), vgg.classifier[0].weight)
+
+
+def test_host_metrics_equal_live_reference():
+    """utils.label_accuracy_score (numpy path) against the unmodified reference, when its checkout is present."""
+    import numpy as np
+    from oracle import ref_import
+    if ref_import.reference_root() is None:
+        pytest.skip("reference checkout not present (GPU box)")
+    _, RU = ref_import.load_reference()
+    import zeroshotsemanticsegmentation_b200 as szn
+    rng = np.random.RandomState(3)
+    for n_class, unseen in ((21, [3, 17]), (33, None)):
+        lt = [rng.randint(-1, n_class, (40, 30)) for _ in range(2)]
+        lp = [np.where(rng.rand(40, 30) < 0.7, np.clip(t, 0, None), rng.randint(0, n_class, (40, 30))) for t in lt]
+        a = szn.utils.label_accuracy_score(lt, lp, n_class, unseen)
+        b = RU.label_accuracy_score(lt, lp, n_class, unseen)
+        np.testing.assert_allclose(np.array(a, dtype=np.float64), np.array(b, dtype=np.float64), rtol=1e-12)

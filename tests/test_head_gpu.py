@@ -93,3 +93,22 @@ def test_argmax_vs_oracle_seeded(shape):
         margin = (top2[:, 0] - top2[:, 1]).numpy()
         assert (margin[mism] < 1e-5).all(), "label mismatch away from a near-tie"
     assert mism.mean() < 1e-4
+
+
+@pytest.mark.parametrize("n_class,unseen", [(21, [3, 17]), (59, list(range(49, 59))), (33, None), (256, [0, 255])])
+def test_device_metrics_equal_reference_formulas(n_class, unseen):
+    """label_accuracy_score on device-resident labels: identical histograms, hence identical scores (utils.py:104-154)."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    g = torch.Generator().manual_seed(17)
+    lt = torch.randint(-1, n_class, (3, 61, 47), generator=g)
+    lp = torch.randint(0, n_class, (3, 61, 47), generator=g)
+    lp[lt >= 0] = torch.where(torch.rand(lt.shape, generator=g) < 0.6, lt, lp)[lt >= 0]  # mostly right, like a trained net
+    hist = U.confusion_hist_device(lt.to(DEV), lp.to(DEV), n_class, unseen).cpu().numpy()
+    want_all = O.fast_hist(lt.numpy().ravel(), lp.numpy().ravel(), n_class)
+    assert (hist[0] == want_all).all()
+    got = U.label_accuracy_score(lt.to(DEV), lp.to(DEV), n_class, unseen)
+    ref = U.label_accuracy_score([a for a in lt.numpy()], [a for a in lp.numpy()], n_class, unseen)  # numpy path = reference code
+    np.testing.assert_allclose(np.array(got, dtype=np.float64), np.array(ref, dtype=np.float64), rtol=0, atol=0)
+    if unseen:
+        assert (hist[1] + hist[2] == hist[0]).all()
+    assert np.allclose(got[0] if unseen else got, O.hist_to_metrics(want_all), equal_nan=True)

@@ -40,6 +40,7 @@ SIGNATURES = {
     "szn_loss_finalize": [I, P, P, P],
     "szn_embed_argmax": [P, P, I, I, I, I, I, P, P, P],
     "szn_stitch_labels": [P, P, P, P, P, I, I, I, I, P, P],
+    "szn_confusion_hist": [P, P, LL, I, P, P, P],
 }
 
 F32, BF16 = 0, 1

@@ -200,8 +200,32 @@ def _hist_to_metrics(hist):
         return acc, acc_cls, np.nanmean(iu), (freq[freq > 0] * iu[freq > 0]).sum()
 
 
+def confusion_hist_device(label_true, label_pred, n_class, unseen=None):
+    """Confusion matrices of ``_fast_hist`` (``utils.py:104-121``) for CUDA label tensors, built on the device.
+    Returns an int64 CUDA tensor (1 or 3, n_class, n_class): target 'all' [, 'seen', 'unseen']."""
+    _check_cuda(label_true, label_pred)
+    lt = label_true.detach().contiguous().long().view(-1)
+    lp = label_pred.detach().contiguous().long().view(-1)
+    flags = None
+    if unseen:
+        flags = torch.zeros(n_class, dtype=torch.uint8, device=lt.device)
+        flags[torch.as_tensor(list(unseen), device=lt.device, dtype=torch.long)] = 1
+    hist = torch.zeros((3 if unseen else 1, n_class, n_class), dtype=torch.int64, device=lt.device)
+    call("szn_confusion_hist", ptr(lt), ptr(lp), lt.numel(), n_class, ptr(flags), ptr(hist), _lib.stream())
+    return hist
+
+
 def label_accuracy_score(label_trues, label_preds, n_class, unseen=None):
-    """Pixel accuracy, mean class accuracy, mean IU, frequency-weighted IU (``utils.py:133-154``)."""
+    """Pixel accuracy, mean class accuracy, mean IU, frequency-weighted IU (``utils.py:133-154``).
+    Accepts the reference's numpy label maps, or CUDA tensors (a tensor or a sequence of tensors): then the histograms
+    are built on the device and only n_class^2 counters are copied to the host."""
+    first = label_trues[0] if isinstance(label_trues, (list, tuple)) else label_trues
+    if isinstance(first, torch.Tensor) and first.is_cuda:
+        lts = label_trues if isinstance(label_trues, (list, tuple)) else [label_trues]
+        lps = label_preds if isinstance(label_preds, (list, tuple)) else [label_preds]
+        hist = sum(confusion_hist_device(a, b, n_class, unseen) for a, b in zip(lts, lps)).cpu().numpy().astype(np.float64)
+        res = [_hist_to_metrics(h) for h in hist]
+        return res[0] if not unseen else tuple(res)
     kinds = ["all"] + (["seen", "unseen"] if unseen else [])
     hists = {k: np.zeros((n_class, n_class)) for k in kinds}
     for lt, lp in zip(label_trues, label_preds):
