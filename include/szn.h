@@ -126,6 +126,12 @@ int szn_stitch_labels(const long long* lbl_seen, const long long* lbl_unseen, co
                       const long long* target, const long long* unseen, int n_unseen, int n, int h, int w,
                       long long* out, void* stream);
 
+/* ---- optimizer step (train.py:126-129 SGD param groups; trainer_fcn.py:158 optim.step()) ----
+ * One fused pass over a parameter's storage: d = g + wd*p; buf = first ? d : momentum*buf + d; p -= lr*buf.
+ * param / grad / momentum_buf: n fp32 values in the SAME memory order (all three dense, same strides). */
+int szn_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
+                 float weight_decay, int first_step, void* stream);
+
 /* ---- metrics (utils.py:104-154, called after every iteration: trainer_fcn.py:164,223,248) ----
  * Confusion matrices of _fast_hist for target = 'all' (and 'seen' / 'unseen' when is_unseen[n_class] is given), built on
  * the device-resident label maps.  hist: int64 [1 or 3][n_class][n_class], accumulated into (zero it first). */

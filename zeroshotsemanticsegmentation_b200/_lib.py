@@ -41,6 +41,7 @@ SIGNATURES = {
     "szn_embed_argmax": [P, P, I, I, I, I, I, P, P, P],
     "szn_stitch_labels": [P, P, P, P, P, I, I, I, I, P, P],
     "szn_confusion_hist": [P, P, LL, I, P, P, P],
+    "szn_sgd_step": [P, P, P, LL, ctypes.c_float, ctypes.c_float, ctypes.c_float, I, P],
 }
 
 F32, BF16 = 0, 1

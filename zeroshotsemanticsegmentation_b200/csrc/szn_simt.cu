@@ -443,6 +443,31 @@ __global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, l
     out[i] = from_float<T>(in[i]);
 }
 
+// torch.optim.SGD step (train.py:126-129: momentum .99, weight_decay 5e-4, biases lr x2 / no decay), one fused pass:
+//   d = g + wd * p;  buf = first ? d : momentum * buf + d;  p -= lr * buf        (dampening 0, no Nesterov)
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                  long long n, float lr, float momentum, float wd, int first) {
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(m)[i];
+    float d;
+    d = fmaf(wd, pv.x, gv.x), mv.x = first ? d : fmaf(momentum, mv.x, d), pv.x = fmaf(-lr, mv.x, pv.x);
+    d = fmaf(wd, pv.y, gv.y), mv.y = first ? d : fmaf(momentum, mv.y, d), pv.y = fmaf(-lr, mv.y, pv.y);
+    d = fmaf(wd, pv.z, gv.z), mv.z = first ? d : fmaf(momentum, mv.z, d), pv.z = fmaf(-lr, mv.z, pv.z);
+    d = fmaf(wd, pv.w, gv.w), mv.w = first ? d : fmaf(momentum, mv.w, d), pv.w = fmaf(-lr, mv.w, pv.w);
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(p)[i] = pv;
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = fmaf(wd, p[i], g[i]);
+    const float b = first ? d : fmaf(momentum, m[i], d);
+    m[i] = b;
+    p[i] = fmaf(-lr, b, p[i]);
+  }
+}
+
 static int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -553,6 +578,15 @@ extern "C" int szn_unpack_wgrad(const float* dw_ohwi, float* g_oihw, int O, int 
 extern "C" int szn_dropout_scale(float* scale, int n, unsigned long long seed, void* stream) {
   dropout_scale_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scale, n, seed);
   return check_launch("szn_dropout_scale");
+}
+
+extern "C" int szn_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
+                            float weight_decay, int first_step, void* stream) {
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(momentum_buf)) & 15)
+    return set_error(SZN_ERR_ARG, "szn_sgd_step: buffers must be 16-byte aligned");
+  sgd_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, n, lr, momentum,
+                                                                        weight_decay, first_step);
+  return check_launch("szn_sgd_step");
 }
 
 extern "C" int szn_cast(int dtype, const float* in, void* out, long long n, void* stream) {
