@@ -78,3 +78,28 @@ def test_host_metrics_equal_live_reference():
         a = szn.utils.label_accuracy_score(lt, lp, n_class, unseen)
         b = RU.label_accuracy_score(lt, lp, n_class, unseen)
         np.testing.assert_allclose(np.array(a, dtype=np.float64), np.array(b, dtype=np.float64), rtol=1e-12)
+
+
+def test_checkpoint_dict_round_trip(tmp_path):
+    """The reference's checkpoint format (trainer_fcn.py:281-292) and resume path (train.py:110-116,135-136):
+    a dict with model_state_dict / optim_state_dict, loaded with load_state_dict(strict=False)."""
+    import zeroshotsemanticsegmentation_b200 as szn
+    from oracle import szn_oracle as O
+    m = szn.FCN32s(n_class=20)
+    m.load_state_dict(O.init_params(20, seed=3))
+    optim = torch.optim.SGD([{"params": [m.conv1_2.weight]}, {"params": [m.conv1_2.bias], "lr": 2e-3, "weight_decay": 0}],
+                            lr=1e-3, momentum=0.99, weight_decay=5e-4)
+    path = str(tmp_path / "checkpoint")
+    torch.save({"epoch": 3, "iteration": 1234, "arch": m.__class__.__name__, "optim_state_dict": optim.state_dict(),
+                "model_state_dict": m.state_dict(), "best_mean_iu": 0.25}, path)
+    ck = torch.load(path)
+    assert ck["arch"] == "FCN32s"
+    m2 = szn.FCN32s(n_class=20)
+    missing = m2.load_state_dict(ck["model_state_dict"], strict=False)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, m2.state_dict()[k]), k
+    # the kernel-friendly (channels_last) parameter layout survives loading; shapes and values are the reference's
+    assert m2.conv3_2.weight.is_contiguous(memory_format=torch.channels_last) and m2.conv3_2.weight.shape == (256, 256, 3, 3)
+    # a reference checkpoint has exactly these 36 tensors
+    assert len(ck["model_state_dict"]) == 36
