@@ -37,13 +37,13 @@ template <typename T>
 __global__ void __launch_bounds__(128) conv1_1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*OIHW [64][3][3][3]*/,
                                                           const float* __restrict__ bias, T* __restrict__ y, int B, int H,
                                                           int W, int Ho, int Wo, int pad) {
-  __shared__ __align__(16) float sw[27 * 64];  // [k][co]
+  __shared__ __align__(16) float sw_[27 * 64];  // [k][co]
   __shared__ float sb[64];
   __shared__ __align__(16) T tile[128 * 64];
   for (int i = threadIdx.x; i < 27 * 64; i += 128) {
     const int co = i & 63, k = i >> 6;
     const int tap = k / 3, c = k - tap * 3;
-    sw[k * 64 + co] = w[co * 27 + c * 9 + tap];  // OIHW -> [tap][ci] order
+    sw_[k * 64 + co] = w[co * 27 + c * 9 + tap];  // OIHW -> [tap][ci] order
   }
   if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
@@ -67,36 +67,58 @@ __global__ void __launch_bounds__(128) conv1_1_fwd_kernel(const float* __restric
         for (int c = 0; c < 3; ++c)
           in[(r * 3 + s) * 3 + c] = ok ? __ldg(x + (((long long)b * 3 + c) * H + yi) * W + xi) : 0.f;
       }
-    T* trow = tile + threadIdx.x * 64;
+    // the thread's 64 channels go to row threadIdx.x of the tile as 16-byte chunks, chunk c stored at c ^ (row & (NCH-1)):
+    // a plain [row][channel] layout makes all 32 lanes hit the same bank (row stride = a multiple of 128 bytes)
+    constexpr int NCH = 64 * sizeof(T) / 16;  // 16-byte chunks per row: 16 (fp32) / 8 (bf16)
+    constexpr int PER = 16 / sizeof(T);       // channels per chunk
+    uint4* trow = reinterpret_cast<uint4*>(tile) + threadIdx.x * NCH;
+    const int sw = threadIdx.x & (NCH - 1);
     if (!any) {
-#pragma unroll 8
-      for (int co = 0; co < 64; ++co) trow[co] = from_float<T>(fmaxf(sb[co], 0.f));
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint4 u;
+        T* e = reinterpret_cast<T*>(&u);
+#pragma unroll
+        for (int j = 0; j < PER; ++j) e[j] = from_float<T>(fmaxf(sb[c * PER + j], 0.f));
+        trow[c ^ sw] = u;
+      }
     } else {
 #pragma unroll 2
-      for (int c4 = 0; c4 < 64; c4 += 4) {
-        float a0 = sb[c4], a1 = sb[c4 + 1], a2 = sb[c4 + 2], a3 = sb[c4 + 3];
+      for (int c = 0; c < NCH; ++c) {
+        uint4 u;
+        T* e = reinterpret_cast<T*>(&u);
 #pragma unroll
-        for (int k = 0; k < 27; ++k) {
-          const float4 wv = *reinterpret_cast<const float4*>(sw + k * 64 + c4);
-          a0 = fmaf(in[k], wv.x, a0);
-          a1 = fmaf(in[k], wv.y, a1);
-          a2 = fmaf(in[k], wv.z, a2);
-          a3 = fmaf(in[k], wv.w, a3);
+        for (int q = 0; q < PER; q += 4) {
+          const int c4 = c * PER + q;
+          float a0 = sb[c4], a1 = sb[c4 + 1], a2 = sb[c4 + 2], a3 = sb[c4 + 3];
+#pragma unroll
+          for (int k = 0; k < 27; ++k) {
+            const float4 wv = *reinterpret_cast<const float4*>(sw_ + k * 64 + c4);
+            a0 = fmaf(in[k], wv.x, a0);
+            a1 = fmaf(in[k], wv.y, a1);
+            a2 = fmaf(in[k], wv.z, a2);
+            a3 = fmaf(in[k], wv.w, a3);
+          }
+          e[q] = from_float<T>(fmaxf(a0, 0.f));
+          e[q + 1] = from_float<T>(fmaxf(a1, 0.f));
+          e[q + 2] = from_float<T>(fmaxf(a2, 0.f));
+          e[q + 3] = from_float<T>(fmaxf(a3, 0.f));
         }
-        trow[c4] = from_float<T>(fmaxf(a0, 0.f));
-        trow[c4 + 1] = from_float<T>(fmaxf(a1, 0.f));
-        trow[c4 + 2] = from_float<T>(fmaxf(a2, 0.f));
-        trow[c4 + 3] = from_float<T>(fmaxf(a3, 0.f));
+        trow[c ^ sw] = u;
       }
     }
   }
   __syncthreads();
   long long npix = total - p0;
   if (npix > 128) npix = 128;
-  const int n16 = (int)(npix * 64 * sizeof(T) / 16);
+  constexpr int NCH2 = 64 * sizeof(T) / 16;
+  const int n16 = (int)(npix * NCH2);
   uint4* dst = reinterpret_cast<uint4*>(y + p0 * 64);
   const uint4* src = reinterpret_cast<const uint4*>(tile);
-  for (int i = threadIdx.x; i < n16; i += 128) dst[i] = src[i];
+  for (int i = threadIdx.x; i < n16; i += 128) {
+    const int row = i / NCH2, c = i - row * NCH2;
+    __stcs(dst + i, src[row * NCH2 + (c ^ (row & (NCH2 - 1)))]);
+  }
 }
 
 // conv1_1 weight gradient: dw[64][27] += sum_pixels dy[p][co] * x[p + tap - pad][ci]   (fp32 atomics)
