@@ -131,7 +131,7 @@ def cpu_oracle_step_fn(cfg):
         loss = O.cosine_loss(f, lab, O.target_embed_from_labels(lab, table))
         loss.backward()
         O.infer_lbl(f.detach(), table)
-        return float(loss)
+        return float(loss.detach())
     return step, torch.get_num_threads()
 
 
