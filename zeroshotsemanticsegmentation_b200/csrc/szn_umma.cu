@@ -36,6 +36,7 @@ struct UmmaParams {
   int Cin;      // MODE 2: channels per tap inside the N index
   int block_n, n_tiles, m_tiles, stages, splits, tmem_cols;
   int total_tiles;  // n_tiles * m_tiles (* splits): work items of the persistent tile loop
+  int m_fast;  // MODE 0: tile order (0: N tiles fastest, share A through L2; 1: M tiles fastest, share the weight slice)
   int mpair;  // MODE 2: 128-row output sub-tiles per work item (2: two accumulators share every B stage)
   int nbuf;   // accumulator buffers in TMEM (2 unless one tile needs all 512 columns)
   int nacc, acc_cols;  // accumulators per tile (K steps round-robin over them) and their TMEM column stride
@@ -88,8 +89,13 @@ struct TileCoord {
 template <int MODE>
 __device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) {
   TileCoord t;
-  const int n_tile = tile % p.n_tiles;
-  int idx = tile / p.n_tiles;
+  int n_tile, idx;
+  if (MODE == 0 && p.m_fast) {  // pixel tiles fastest: CTAs running side by side share the B (weight) slice instead
+    const int mt = p.total_tiles / p.n_tiles;
+    n_tile = tile / mt, idx = tile - n_tile * mt;
+  } else {
+    n_tile = tile % p.n_tiles, idx = tile / p.n_tiles;
+  }
   t.n0 = n_tile * p.block_n;
   t.b = t.x0 = t.y0 = t.m0 = t.q_begin = 0;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -727,6 +733,14 @@ static int conv_gemm(int dtype, const void* x, long long ldx, const void* wt, co
     if (int e = make_tmap(&tb, dtype, wt, 2, d2, s2, bx2)) return e;
   }
   const long long tiles = (long long)p.tiles_x * p.tiles_y * Bq * p.n_tiles;
+  {
+    // Which operand should concurrently running CTAs share through L2?  By default the pixel tile (N tiles fastest).
+    // When the weights are far larger than L2 while the activations fit (fc6's data gradient: 411 MB of weights, 38 MB
+    // of dY), N-fastest makes every M tile re-stream all weights from HBM; M-fastest reads each weight slice once.
+    const double es = dtype == SZN_BF16 ? 2.0 : 4.0;
+    const double w_bytes = (double)R * S * Cin * Cout * es, a_bytes = (double)B * H * W * Cin * es;
+    p.m_fast = (w_bytes > 96e6 && a_bytes < 64e6 && p.n_tiles > 1) ? 1 : 0;
+  }
   return dtype == SZN_BF16 ? launch<__nv_bfloat16, 0>(ta, tb, to, p, tiles, (cudaStream_t)stream)
                            : launch<float, 0>(ta, tb, to, p, tiles, (cudaStream_t)stream);
 }
