@@ -1,18 +1,11 @@
 #!/bin/bash
-# One GPU session: kernel-level parity tests in isolated processes (a trap in one group cannot poison the others).
+# One GPU session (run through gpurun): parity tests, smoke, default bench and the ncu launch list.  Every step has its
+# own short timeout: a hung kernel must not eat the GPU budget.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-run() { # name, pytest args...
-  local name=$1; shift
-  timeout 300 python -m pytest "$@" -q --timeout 120 -s > gpurun_out/$name.log 2>&1
-  echo "$name exit=$? :: $(tail -1 gpurun_out/$name.log)"
-  grep -E "relerr|rel err|^FAILED|^ERROR" gpurun_out/$name.log | head -40
-}
-run k_fwd   tests/test_kernels_gpu.py -k "test_conv_fwd"
-run k_dgrad tests/test_kernels_gpu.py -k "test_conv_dgrad"
-run k_wgrad tests/test_kernels_gpu.py -k "test_conv_wgrad"
-run k_misc  tests/test_kernels_gpu.py -k "conv1_1 or pool or bias_grad or upsample"
-run head    tests/test_head_gpu.py
-run model   tests/test_model_gpu.py
-timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit=$? :: $(tail -1 gpurun_out/smoke.log)"
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.log 2>&1; echo "bench exit=$? :: $(tail -c 3000 gpurun_out/bench_quick.log)"
+timeout 400 python -m pytest tests -m gpu -q --timeout 200 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit=$? :: $(tail -1 gpurun_out/pytest_gpu.log)"
+timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit=$? :: $(tail -1 gpurun_out/smoke.log)"
+timeout 400 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench exit=$? :: $(tail -c 400 gpurun_out/bench_default.log)"
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
+python tools/launch_summary.py gpurun_out/launches.csv > gpurun_out/launches_summary.txt 2>&1; head -20 gpurun_out/launches_summary.txt

@@ -1,23 +1,29 @@
 // tcgen05 implicit-GEMM convolution kernels for sm_100a (forward, data-gradient, weight-gradient).
 //
-// One warp-specialised kernel template covers the three GEMM shapes of the VGG16-FCN32s trunk
+// One persistent, warp-specialised kernel template covers the GEMM shapes of the VGG16-FCN32s trunk
 // (reference: models.py:43-98 forward, autograd backward of the same layers):
 //
 //   MODE 0  forward   D[pixel, co] = sum_{tap, ci} X[pixel + tap - pad, ci] * Wt[co, tap, ci]
 //           A = activations, K-major (NHWC: channels contiguous), loaded as 4-D TMA boxes
 //               (KC channels x TW x TH pixels) at the tap-shifted coordinate; out-of-image pixels are
-//               zero-filled by TMA, which implements the conv padding (pad=1, and pad=6 of the fc6 dgrad).
+//               zero-filled by TMA, which implements the conv padding.
 //           B = weights [Cout][taps*Cin], K-major, 2-D TMA boxes.
 //           dgrad runs on the same path: it is the forward conv of dY with the transposed, flipped weights
-//           (szn_pack_weight_dgrad) and padding R-1-pad; its epilogue fuses the ReLU gate and the Dropout2d scale.
+//           (szn_pack_weight_dgrad) and padding R-1-pad; its epilogue fuses the ReLU gate, the Dropout2d scale
+//           and the bias gradient (column sums) of the layer that produced the conv's input.
 //   MODE 2  wgrad     D[co, (tap, ci)] = sum_{pixel} dY[pixel, co] * X[pixel + tap - pad, ci]
-//           both operands MN-major (the reduction runs over pixels), split-K over pixel chunks,
-//           fp32 atomics into dW[Cout][taps*Cin].
+//           both operands MN-major (the reduction runs over pixels), fetched with 5-D TMA boxes (one box lands all
+//           128-byte channel groups of an operand), split-K over pixel chunks, reduced into dW[Cout][taps*Cin] by
+//           TMA fp32 reduce-add; two 128-row output sub-tiles share every B stage when Cout >= 256.
 //
 // Tiles: UMMA M = 128 (rows = pixels of a TW x TH patch, or output channels for wgrad), N = block_n
 // (32..256), K per stage = 128 bytes of the contraction dim (64 bf16 / 32 tf32), SWIZZLE_128B smem
-// layouts written by TMA and consumed through shared-memory descriptors, fp32 accumulators in TMEM.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM -> regs -> HBM).
+// layouts (SWIZZLE_128B_BASE32B for tf32 MN-major) written by TMA and consumed through shared-memory
+// descriptors, fp32 accumulators in TMEM (two buffers: the epilogue of a tile overlaps the next main loop).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
+// (TMEM -> registers -> swizzled staging rows -> TMA store / reduce-add).  192 threads, one CTA per SM.
+// Debug hooks (never set in production): SZN_DBG / SZN_DBG_MODE skip operand loads or stores for timing
+// experiments, SZN_TRACE records clock64 stamps of CTA 0's roles (tools/trace_tiles.py).
 #include "szn_internal.h"
 #include "szn_ptx.cuh"
 #include <stdlib.h>

@@ -7,7 +7,10 @@ Follows the reference layer sequence (``models.py:114-160``) and what autograd d
 Data layout in HBM
   * image ``x``: NCHW fp32 (public API, read once by ``szn_conv1_1_fwd``);
   * trunk activations: NHWC, element type = precision (``tf32``: fp32 rounded to TF32, ``bf16``);
-  * packed weights ``[Cout][R*S][Cin]`` in the activation type, cached per parameter version;
+  * packed weights in the activation type, cached per parameter version: ``[Cout][R*S][Cin]`` for the forward pass,
+    ``[Cin][R*S flipped][Cout]`` for the data gradient (fc6: ``[R*S*Cin][Cout]`` + ``szn_col2im``);
+  * conv parameters live in channels_last memory, so the wgrad kernel's ``[Cout][R][S][Cin]`` fp32 output buffer is
+    handed to autograd as ``weight.grad`` without a transposing pass;
   * head: ``s17`` = fp32 ``[B,hs,ws,Dp]`` holding ``score_fr`` (channels 0..D-1) and ``seenmask_score``
     (channels D, D+1) from ONE GEMM, ``Dp`` = D+2 rounded up to 64;
   * returned ``f`` (B,D,H,W) / ``s`` (B,2,H,W): NCHW fp32 contiguous, as the reference returns them.
