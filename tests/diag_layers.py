@@ -1,4 +1,5 @@
-"""Layer-by-layer comparison of the CUDA path with the storage-precision oracle (debug aid, GPU box)."""
+"""Layer-by-layer comparison of the CUDA path with the storage-precision oracle (debug aid for the GPU box; lives under
+tests/ because only test infrastructure may import oracle/).  usage: python tests/diag_layers.py [tf32|bf16]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
