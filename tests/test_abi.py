@@ -103,3 +103,18 @@ def test_checkpoint_dict_round_trip(tmp_path):
     assert m2.conv3_2.weight.is_contiguous(memory_format=torch.channels_last) and m2.conv3_2.weight.shape == (256, 256, 3, 3)
     # a reference checkpoint has exactly these 36 tensors
     assert len(ck["model_state_dict"]) == 36
+
+
+def test_seen_unseen_helpers_match_oracle():
+    """utils.split_embeddings / seenmask_target vs the oracle's restatement of trainer_fcn.py:44-64 and
+    trainer_seenmask.py:55-56 (host logic, any device)."""
+    import zeroshotsemanticsegmentation_b200 as szn
+    from oracle import szn_oracle as O
+    g = torch.Generator().manual_seed(5)
+    table = torch.randn(21, 20, generator=g)
+    unseen = [3, 17, 20]
+    a, b = szn.utils.split_embeddings(table, unseen)
+    ra, rb = O.split_tables(table, unseen)
+    assert torch.equal(a, ra) and torch.equal(b, rb)
+    t = torch.randint(-1, 21, (2, 9, 7), generator=g)
+    assert torch.equal(szn.utils.seenmask_target(t, unseen, 21), O.seenmask_target(t, unseen, 21))

@@ -35,6 +35,28 @@ def save_obj(obj, name):
         pickle.dump(obj, f, pickle.HIGHEST_PROTOCOL)
 
 
+def split_embeddings(embed_arr, unseen):
+    """Seen / unseen copies of the (C, D) class table with the other set's rows zeroed, as ``trainer_fcn.Trainer``
+    builds them (``trainer_fcn.py:44,55-64``).  A zero row scores exactly 0 in ``infer_lbl`` (``utils.py:175``)."""
+    table = torch.as_tensor(embed_arr).float()
+    unseen = sorted(set(int(u) for u in unseen))
+    seen = [c for c in range(table.shape[0]) if c not in unseen]
+    seen_t, unseen_t = torch.zeros_like(table), torch.zeros_like(table)
+    seen_t[seen] = table[seen]
+    unseen_t[unseen] = table[unseen]
+    return seen_t, unseen_t
+
+
+def seenmask_target(target, unseen, n_class):
+    """Binary target of the seen-mask phase (``trainer_seenmask.py:53-56``): 1 where the label is a seen class, else 0
+    (the ignore label -1 therefore becomes 0 and is NOT ignored, as upstream).  Works on the tensor's own device, so the
+    label map need not visit the host."""
+    unseen = torch.as_tensor(sorted(set(int(u) for u in unseen)), dtype=torch.long, device=target.device)
+    t = target.long()
+    seen = (t >= 0) & (t < n_class) & ~torch.isin(t, unseen)
+    return seen.long()
+
+
 def _check_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
