@@ -554,7 +554,16 @@ extern "C" int szn_pool_bwd(int dtype, const void* y, const void* dp, void* dy, 
   if (C % vn) return set_error(SZN_ERR_ARG, "szn_pool_bwd: C must be a multiple of 16 bytes");
   const long long total = (long long)B * Ho * Wo * (C / vn);
   if (dy_col_sum && 256 % (C / vn)) return set_error(SZN_ERR_UNSUPPORTED, "szn_pool_bwd: fused channel sums need C/vector to divide 256");
-  DISPATCH_T(dtype, (pool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)y, (const T*)dp, (T*)dy, B, H, W, C, Ho, Wo, relu_gate, dy_col_sum)));
+  int grid = grid_for(total, 256);
+  {
+    static int cap = 0;  // with fused channel sums every block ends with C atomics: fewer, longer-lived blocks
+    if (!cap) {
+      const char* e = getenv("SZN_POOL_BLOCKS");
+      cap = e ? atoi(e) : 148 * 4;
+    }
+    if (dy_col_sum && grid > cap) grid = cap;
+  }
+  DISPATCH_T(dtype, (pool_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)y, (const T*)dp, (T*)dy, B, H, W, C, Ho, Wo, relu_gate, dy_col_sum)));
   return check_launch("szn_pool_bwd");
 }
 

@@ -831,7 +831,15 @@ extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* d
   p.m_tiles = ceil_div(Cout, 128 * p.mpair);
   const long long total_q = (long long)p.tiles_x * p.tiles_y * Bq;
   const long long tiles = (long long)p.n_tiles * p.m_tiles;
-  long long splits = (2 * 148 + tiles - 1) / tiles;  // about two waves of CTAs
+  static int waves = 0;
+  if (!waves) {
+    const char* e = getenv("SZN_WGRAD_WAVES");  // tuning hook
+    waves = e ? atoi(e) : 1;  // measured 5.30 / 5.38 / 5.46 / 5.54 ms for 1 / 2 / 3 / 4
+    if (waves < 1) waves = 1;
+  }
+  // `waves` work items per CTA, rounded DOWN so that no CTA gets one item more than the others (rounding up gave
+  // e.g. 297 items for 148 CTAs: one CTA with 3 items set the kernel's duration)
+  long long splits = ((long long)waves * num_sms()) / tiles;
   if (splits > total_q / 4) splits = total_q / 4;    // at least 4 chunks per split
   if (splits < 1) splits = 1;
   p.splits = (int)splits;
