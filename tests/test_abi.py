@@ -118,3 +118,15 @@ def test_seen_unseen_helpers_match_oracle():
     assert torch.equal(a, ra) and torch.equal(b, rb)
     t = torch.randint(-1, 21, (2, 9, 7), generator=g)
     assert torch.equal(szn.utils.seenmask_target(t, unseen, 21), O.seenmask_target(t, unseen, 21))
+
+
+def test_missing_extension_fails_loudly():
+    """No silent fallback: without libszn.so the binding raises (checked in a fresh interpreter)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from zeroshotsemanticsegmentation_b200 import _lib\n"
+            "try:\n    _lib.load()\nexcept RuntimeError as e:\n    print('RAISED', 'no CPU fallback' in str(e))\n" % ROOT)
+    env = dict(os.environ, SZN_LIB="/nonexistent/libszn.so")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert "RAISED True" in out.stdout, out.stdout + out.stderr
