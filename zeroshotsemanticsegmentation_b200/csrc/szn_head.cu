@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256, 3) embed_loss_fwd_kernel(const float* __r
 }
 
 template <int KIND, int VEC, bool HAS_TE>
-__global__ void __launch_bounds__(256, 3) embed_loss_bwd_kernel(const float* __restrict__ score, const long long* __restrict__ target,
+__global__ void __launch_bounds__(256, 2) embed_loss_bwd_kernel(const float* __restrict__ score, const long long* __restrict__ target,
                                                              const float* __restrict__ te, const float* __restrict__ table,
                                                              int n, int c, long long hw, const float* __restrict__ stats,
                                                              const double* __restrict__ accum, const float* __restrict__ gout,
@@ -384,24 +384,36 @@ __global__ void __launch_bounds__(256, 3) embed_loss_bwd_kernel(const float* __r
       inv_s[j] = st[0], inv_e[j] = st[1], cs[j] = st[2];
     }
   }
-#pragma unroll 8
-  for (int d = 0; d < c; ++d) {
-    const PixVec<VEC> sv = ld_pix<VEC>(sp + d * hw);
-    PixVec<VEC> ev, gv;
-    if (HAS_TE) {
-      ev = ld_pix<VEC>(ep + d * hw);
-    } else {
+  // Explicit batches of 8 channels: all 8 (or 16) vector loads are issued before the first store.  Written as one
+  // load-compute-store per channel, the cache-hinted loads were kept in program order behind the previous channel's
+  // store (one 16-byte load in flight per thread: 4.1 TB/s).
+  constexpr int UNR = 8;
+  for (int d0 = 0; d0 < c; d0 += UNR) {
+    PixVec<VEC> sv[UNR], ev[UNR];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) ev.v[j] = __ldg(tp[j] + d);
+    for (int u = 0; u < UNR; ++u) {
+      const int d = d0 + u < c ? d0 + u : c - 1;  // the tail re-reads the last channel (never stored twice)
+      sv[u] = ld_pix<VEC>(sp + d * hw);
+      if (HAS_TE) {
+        ev[u] = ld_pix<VEC>(ep + d * hw);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) ev[u].v[j] = __ldg(tp[j] + d);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float g;
-      if (KIND == 0) g = -gs * (ev.v[j] * inv_e[j] - cs[j] * sv.v[j] * inv_s[j]) * inv_s[j];  // d(-cos)/ds
-      else g = 2.f * gs * (sv.v[j] - ev.v[j]);
-      gv.v[j] = live[j] != 0.f ? g : 0.f;
+    for (int u = 0; u < UNR; ++u) {
+      if (d0 + u >= c) break;
+      PixVec<VEC> gv;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float g;
+        if (KIND == 0) g = -gs * (ev[u].v[j] * inv_e[j] - cs[j] * sv[u].v[j] * inv_s[j]) * inv_s[j];  // d(-cos)/ds
+        else g = 2.f * gs * (sv[u].v[j] - ev[u].v[j]);
+        gv.v[j] = live[j] != 0.f ? g : 0.f;
+      }
+      st_pix<VEC>(gp + (d0 + u) * hw, gv);
     }
-    st_pix<VEC>(gp + d * hw, gv);
   }
 }
 
