@@ -47,7 +47,10 @@ int szn_conv_fwd(int dtype, const void* x, const void* wt, const float* bias, vo
 int szn_conv_dgrad(int dtype, const void* dy, const void* wt_dgrad, void* dx, int B, int H, int W, int Cin, int Cout,
                    int R, int S, int pad, const void* relu_ref, const float* scale, int scale_ld, long long ld_dy,
                    float* dx_col_sum, void* stream);
-/* dw[Cout][R*S*Cin] += sum_pixels dy (x) x   (fp32, split-K atomics: zero dw first) */
+/* dw[Cout][R*S*Cin] += sum_pixels dy (x) x   (fp32; split-K partial tiles are added with TMA reduce-add: zero dw first).
+ * Cin, Cout and ld_dy must be multiples of 128 bytes of the element type (32 fp32 / 64 bf16).  The buffer is the
+ * channels_last image of the OIHW gradient, so it can be handed to autograd as weight.grad of a channels_last parameter
+ * without a transposing pass (trainer_fcn.py:157 loss.backward()). */
 int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int R,
                    int S, int pad, long long ld_dy, void* stream);
 
@@ -65,7 +68,8 @@ int szn_pool_fwd(int dtype, const void* in, void* out, int B, int H, int W, int 
 int szn_pool_bwd(int dtype, const void* y, const void* dp, void* dy, int B, int H, int W, int C, int relu_gate,
                  float* dy_col_sum, void* stream);
 
-/* db[C] += column sums of dy[rows][ld]  (bias gradients of every conv; zero db first) */
+/* db[C] += column sums of dy[rows][ld]  (stand-alone bias gradient; the conv layers get theirs fused into
+ * szn_conv_dgrad / szn_pool_bwd, this entry point serves the 17x17 score heads; zero db first) */
 int szn_bias_grad(int dtype, const void* dy, float* db, long long rows, int C, long long ld, void* stream);
 
 /* parameter layout conversion between the reference's OIHW fp32 tensors (state_dict layout, models.py:43-98)
