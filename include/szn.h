@@ -136,6 +136,13 @@ int szn_stitch_labels(const long long* lbl_seen, const long long* lbl_unseen, co
 int szn_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
                  float weight_decay, int first_step, void* stream);
 
+/* Adam (train.py:130-133 optional FCN optimizer, train.py:175 seen-mask phase: torch.optim.Adam(params, lr)), amsgrad off.
+ * g' = g + wd*p; m += (1-b1)(g'-m); v = b2*v + (1-b2)g'^2; p -= step_size * m / (sqrt(v)/bias_correction2_sqrt + eps),
+ * with step_size = lr / (1 - b1^t) and bias_correction2_sqrt = sqrt(1 - b2^t) formed by the caller for step t >= 1.
+ * param / grad / exp_avg / exp_avg_sq: n fp32 values in the SAME memory order, 16-byte aligned. */
+int szn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float beta1, float beta2,
+                  float eps, float weight_decay, float step_size, float bias_correction2_sqrt, void* stream);
+
 /* ---- metrics (utils.py:104-154, called after every iteration: trainer_fcn.py:164,223,248) ----
  * Confusion matrices of _fast_hist for target = 'all' (and 'seen' / 'unseen' when is_unseen[n_class] is given), built on
  * the device-resident label maps.  hist: int64 [1 or 3][n_class][n_class], accumulated into (zero it first). */

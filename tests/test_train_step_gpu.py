@@ -61,6 +61,51 @@ def test_fused_sgd_equals_torch_sgd():
     assert all("momentum_buffer" in s for s in ref2.state_dict()["state"].values())
 
 
+def test_fused_adam_equals_torch_adam():
+    """train.py:133 / :175: torch.optim.Adam(params, lr) with the bias group at lr * 2."""
+    from zeroshotsemanticsegmentation_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(2)
+    shapes = [(2, 4096, 1, 1), (2,), (2, 2, 64, 64), (64, 32, 3, 3), (33,)]
+    ref_p, my_p = [], []
+    for i, s in enumerate(shapes):
+        t = torch.randn(s, generator=g)
+        a, b = t.clone().to(DEV), t.clone().to(DEV)
+        if s == (64, 32, 3, 3):
+            a = a.contiguous(memory_format=torch.channels_last)
+            b = b.contiguous(memory_format=torch.channels_last)
+        ref_p.append(nn.Parameter(a))
+        my_p.append(nn.Parameter(b))
+    groups = lambda ps: [{"params": ps[::2]}, {"params": ps[1::2], "lr": 2e-3}]
+    for kw in (dict(lr=1e-3), dict(lr=1e-3, betas=(0.8, 0.99), eps=1e-6, weight_decay=1e-2)):
+        ref, mine = torch.optim.Adam(groups(ref_p), **kw), FusedAdam(groups(my_p), **kw)
+        for step in range(5):
+            for a, b in zip(ref_p, my_p):
+                gr = torch.randn(a.shape, generator=g).to(DEV) * (10.0 ** (step - 2))
+                a.grad, b.grad = gr.clone(), gr.clone()
+            ref.step()
+            mine.step()
+            for a, b in zip(ref_p, my_p):
+                assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), (kw, step, (a - b).abs().max().item())
+        # torch's state layout: a FusedAdam checkpoint loads into torch.optim.Adam and continues identically
+        ref2 = torch.optim.Adam(groups(ref_p), **kw)
+        ref2.load_state_dict(mine.state_dict())
+        st = ref2.state_dict()["state"]
+        assert all(set(v) >= {"step", "exp_avg", "exp_avg_sq"} and float(v["step"]) == 5 for v in st.values())
+        mine2 = FusedAdam(groups(my_p), **kw)
+        mine2.load_state_dict(ref.state_dict())
+        for a, b in zip(ref_p, my_p):
+            gr = torch.randn(a.shape, generator=g).to(DEV)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        ref.step()
+        mine2.step()
+        for a, b in zip(ref_p, my_p):
+            assert torch.allclose(a, b, rtol=2e-6, atol=1e-7)
+    cpu_p = nn.Parameter(torch.zeros(3))
+    cpu_p.grad = torch.zeros(3)
+    with pytest.raises(RuntimeError):
+        FusedAdam([cpu_p], lr=1e-3).step()  # no CPU fallback
+
+
 def test_training_iteration_matches_oracle():
     import zeroshotsemanticsegmentation_b200 as szn
     from zeroshotsemanticsegmentation_b200.optim import FusedSGD

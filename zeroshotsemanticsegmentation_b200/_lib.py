@@ -42,6 +42,7 @@ SIGNATURES = {
     "szn_stitch_labels": [P, P, P, P, P, I, I, I, I, P, P],
     "szn_confusion_hist": [P, P, LL, I, P, P, P],
     "szn_sgd_step": [P, P, P, LL, ctypes.c_float, ctypes.c_float, ctypes.c_float, I, P],
+    "szn_adam_step": [P, P, P, P, LL] + [ctypes.c_float] * 6 + [P],
 }
 
 F32, BF16 = 0, 1

@@ -490,6 +490,39 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
   }
 }
 
+// Adam (torch.optim.Adam, amsgrad off): one pass instead of torch's six elementwise passes.  step_size = lr / (1 - b1^t),
+// inv_bc2_sqrt is passed as bc2_sqrt = sqrt(1 - b2^t) and applied as a division, like torch's single-tensor path.
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float b1, float b2, float one_minus_b1,
+                                            float one_minus_b2, float eps, float wd, float step_size, float bc2_sqrt) {
+  g = fmaf(wd, p, g);
+  m = fmaf(one_minus_b1, g - m, m);            // exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(one_minus_b2 * g, g, b2 * v);       // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = sqrtf(v) / bc2_sqrt + eps;
+  p = fmaf(-step_size, m / denom, p);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float b1, float b2, float eps,
+                                                   float wd, float step_size, float bc2_sqrt) {
+  const float omb1 = 1.f - b1, omb2 = 1.f - b2;
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_update(pv.x, gv.x, mv.x, vv.x, b1, b2, omb1, omb2, eps, wd, step_size, bc2_sqrt);
+    adam_update(pv.y, gv.y, mv.y, vv.y, b1, b2, omb1, omb2, eps, wd, step_size, bc2_sqrt);
+    adam_update(pv.z, gv.z, mv.z, vv.z, b1, b2, omb1, omb2, eps, wd, step_size, bc2_sqrt);
+    adam_update(pv.w, gv.w, mv.w, vv.w, b1, b2, omb1, omb2, eps, wd, step_size, bc2_sqrt);
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    reinterpret_cast<float4*>(p)[i] = pv;
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    adam_update(p[i], g[i], m[i], v[i], b1, b2, omb1, omb2, eps, wd, step_size, bc2_sqrt);
+}
+
 static int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -618,6 +651,19 @@ extern "C" int szn_sgd_step(float* param, const float* grad, float* momentum_buf
   sgd_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, n, lr, momentum,
                                                                         weight_decay, first_step);
   return check_launch("szn_sgd_step");
+}
+
+extern "C" int szn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float beta1,
+                             float beta2, float eps, float weight_decay, float step_size, float bias_correction2_sqrt,
+                             void* stream) {
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+       reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+    return set_error(SZN_ERR_ARG, "szn_adam_step: buffers must be 16-byte aligned");
+  if (!(bias_correction2_sqrt > 0.f)) return set_error(SZN_ERR_ARG, "szn_adam_step: bias_correction2_sqrt must be > 0");
+  adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2,
+                                                                         eps, weight_decay, step_size,
+                                                                         bias_correction2_sqrt);
+  return check_launch("szn_adam_step");
 }
 
 extern "C" int szn_cast(int dtype, const float* in, void* out, long long n, void* stream) {

@@ -192,6 +192,18 @@ def infer_lbl_szn(score, seen_mask_score, seen_embed_arr, unseen_embed_arr, cuda
     return _stitch(score, seen_embed_arr, unseen_embed_arr, seen_mask_score=seen_mask_score).cpu().numpy()
 
 
+def infer_lbl_forced_unseen_device(score, target, seen_embed_arr, unseen_embed_arr, unseen):
+    """``infer_lbl_forced_unseen`` that leaves the labels on the device (int64 CUDA tensor (n,h,w))."""
+    _check_cuda(target)
+    return _stitch(score, seen_embed_arr, unseen_embed_arr, target=target, unseen=unseen)
+
+
+def infer_lbl_szn_device(score, seen_mask_score, seen_embed_arr, unseen_embed_arr):
+    """``infer_lbl_szn`` that leaves the labels on the device (int64 CUDA tensor (n,h,w))."""
+    _check_cuda(seen_mask_score)
+    return _stitch(score, seen_embed_arr, unseen_embed_arr, seen_mask_score=seen_mask_score)
+
+
 def stich_seen_unseen_with_mask(score, seen_embed_arr, unseen_embed_arr, unseen_mask, cuda=True):
     """``utils.py:201-205`` with an explicit boolean mask (n,h,w)."""
     pred = infer_lbl(score, seen_embed_arr)
@@ -220,6 +232,17 @@ def _hist_to_metrics(hist):
         iu = tp / (hist.sum(axis=1) + hist.sum(axis=0) - tp)
         freq = hist.sum(axis=1) / hist.sum()
         return acc, acc_cls, np.nanmean(iu), (freq[freq > 0] * iu[freq > 0]).sum()
+
+
+def metrics_from_hist(hist):
+    """(k, n_class, n_class) confusion matrices (device tensor or array) -> k tuples (acc, acc_cls, mean_iu, fwavacc),
+    ``utils.py:123-131``.  Lets a validation loop accumulate one histogram on the device instead of every label map."""
+    if isinstance(hist, torch.Tensor):
+        hist = hist.cpu().numpy()
+    hist = np.asarray(hist, dtype=np.float64)
+    if hist.ndim == 2:
+        hist = hist[None]
+    return tuple(_hist_to_metrics(h) for h in hist)
 
 
 def confusion_hist_device(label_true, label_pred, n_class, unseen=None):
