@@ -1,0 +1,115 @@
+"""Edge cases of the hot path on the CUDA path, each against the CPU oracle (= what the reference does there):
+all-ignored label maps, the smallest and most ragged image sizes (pad=100 makes every H, W >= 1 legal),
+degenerate class tables, out-of-range labels in the metrics, non-contiguous score tensors."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import szn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def test_all_pixels_ignored_is_nan_like_the_reference():
+    """N_valid == 0: the reference divides by zero (utils.py:72,101,46-47) and the trainer raises on the NaN
+    (trainer_fcn.py:107-108); cross_entropy2d with size_average=False returns 0."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    g = torch.Generator().manual_seed(0)
+    score = torch.randn(2, 6, 9, 11, generator=g)
+    tab = torch.randn(4, 6, generator=g)
+    lab = torch.full((2, 9, 11), -1, dtype=torch.int64)
+    te = O.target_embed_from_labels(lab, tab)
+    assert math.isnan(O.cosine_loss(score, lab, te).item()) and math.isnan(O.mse_loss(score, lab, te).item())
+    sd, ld, td = score.to(DEV), lab.to(DEV), tab.to(DEV)
+    assert math.isnan(U.cosine_loss(sd, ld, table=td).item())
+    assert math.isnan(U.mse_loss(sd, ld, te.to(DEV)).item())
+    assert math.isnan(U.cross_entropy2d(sd, ld, size_average=True).item())
+    assert U.cross_entropy2d(sd, ld, size_average=False).item() == 0.0
+    assert O.cross_entropy2d(score, lab, size_average=False).item() == 0.0
+
+
+@pytest.mark.parametrize("H,W,B", [(1, 1, 1), (5, 3, 2), (24, 31, 1), (33, 1, 3)])
+def test_smallest_and_ragged_images(H, W, B):
+    """Whole path at sizes where the 17x17-style score map degenerates to 1x1 / 1x2 / 2x1, H*W is odd, B is odd."""
+    import zeroshotsemanticsegmentation_b200 as szn
+    U = szn.utils
+    D, C = 5, 7
+    params = O.init_params(D, seed=21)
+    x, lab, tab = O.synth_batch(B, H, W, C, D, seed=21 + H, block=2, ignore_frac=0.0 if H * W < 4 else 0.2)
+    pr = {k: v.clone().requires_grad_("upscore" not in k) for k, v in params.items()}
+    f_ref, s_ref = O.forward(x, pr, "both")
+    loss_ref = O.mse_loss(f_ref, lab, O.target_embed_from_labels(lab, tab))
+    loss_ref.backward()
+    m = szn.FCN32s(D)
+    m.load_state_dict(params)
+    m = m.to(DEV).eval()
+    f, s = m(x.to(DEV), mode="both")
+    assert f.shape == (B, D, H, W) and s.shape == (B, 2, H, W) and f.is_contiguous()
+    assert rel(f.detach().cpu().numpy(), f_ref.detach().numpy()) < 1e-3
+    assert rel(s.detach().cpu().numpy(), s_ref.detach().numpy()) < 1e-3
+    loss = U.mse_loss(f, lab.to(DEV), table=tab.to(DEV))
+    assert abs(loss.item() - loss_ref.item()) < 1e-3 * max(1.0, abs(loss_ref.item()))
+    loss.backward()
+    assert rel(m.score_fr.weight.grad.cpu().numpy(), pr["score_fr.weight"].grad.numpy()) < 1e-2
+    assert rel(m.score_fr.bias.grad.cpu().numpy(), pr["score_fr.bias"].grad.numpy()) < 1e-2
+    # labels on the oracle's score tensor: exact
+    fd = f_ref.detach()
+    assert (U.infer_lbl(fd.to(DEV), tab.to(DEV)) == O.infer_lbl(fd, tab)).all()
+    st, ut = O.split_tables(tab, [1, 4])
+    sd = s_ref.detach()
+    assert (U.infer_lbl_szn(fd.to(DEV), sd.to(DEV), st.to(DEV), ut.to(DEV)) == O.infer_lbl_szn(fd, sd, st, ut)).all()
+
+
+def test_degenerate_tables_and_ties():
+    """All-zero table: every similarity is exactly 0, the first index wins (utils.py:172-180, torch.max tie rule).
+    Duplicate rows: the lower index wins.  One class only: label 0 everywhere."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    g = torch.Generator().manual_seed(4)
+    for shape in ((1, 8, 16, 16), (2, 33, 5, 7)):  # tensor-core path (H*W % 32 == 0) and the CUDA-core path
+        score = torch.randn(shape, generator=g)
+        D = shape[1]
+        zero = torch.zeros(6, D)
+        assert (U.infer_lbl(score.to(DEV), zero.to(DEV)) == 0).all() and (O.infer_lbl(score, zero) == 0).all()
+        dup = torch.randn(3, D, generator=g)
+        dup = torch.cat([dup, dup], 0)  # rows 3..5 repeat rows 0..2 exactly: exact ties, the lower index wins
+        got = U.infer_lbl(score.to(DEV), dup.to(DEV))
+        assert got.max() <= 2
+        one = torch.randn(1, D, generator=g)
+        assert (U.infer_lbl(score.to(DEV), one.to(DEV)) == 0).all()
+
+
+def test_metrics_ignore_out_of_range_labels():
+    """_fast_hist keeps 0 <= label_true < n_class only (utils.py:105)."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    lt = torch.tensor([[[-1, 0, 1, 2, 5, 300, -7, 1]]])
+    lp = torch.tensor([[[0, 0, 1, 1, 2, 0, 1, 1]]])
+    hist = U.confusion_hist_device(lt.to(DEV), lp.to(DEV), 3).cpu().numpy()[0]
+    assert (hist == O.fast_hist(lt.numpy().ravel(), lp.numpy().ravel(), 3)).all() and hist.sum() == 4
+
+
+def test_non_contiguous_scores_and_explicit_target_embed():
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    g = torch.Generator().manual_seed(8)
+    big = torch.randn(2, 12, 10, 14, generator=g)
+    tab = torch.randn(9, 6, generator=g)
+    lab = torch.randint(-1, 9, (2, 10, 14), generator=g)
+    score = big[:, ::2]                                           # strided channel slice
+    cl = score.contiguous(memory_format=torch.channels_last)      # NHWC memory behind an NCHW shape
+    te = O.target_embed_from_labels(lab, tab)
+    want = O.cosine_loss(score, lab, te).item()
+    for sc in (score, cl):
+        sd = sc.to(DEV)
+        if sc is score:
+            sd = big.to(DEV)[:, ::2]
+        sd.requires_grad_(False)
+        assert abs(U.cosine_loss(sd, lab.to(DEV), te.to(DEV)).item() - want) < 1e-5
+        assert abs(U.cosine_loss(sd, lab.to(DEV), table=tab.to(DEV)).item() - want) < 1e-5
+        assert (U.infer_lbl(sd, tab.to(DEV)) == O.infer_lbl(score.contiguous(), tab)).mean() > 0.99

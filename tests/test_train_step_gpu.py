@@ -1,5 +1,7 @@
 """One full training iteration in the reference's call order (trainer_fcn.py:83-120 forward, :149-158 train_epoch;
 optimizer groups of train.py:126-129) on the CUDA path with the fused SGD step, against the CPU oracle + torch.optim.SGD."""
+import copy
+
 import numpy as np
 import pytest
 import torch
@@ -92,7 +94,8 @@ def test_fused_adam_equals_torch_adam():
         st = ref2.state_dict()["state"]
         assert all(set(v) >= {"step", "exp_avg", "exp_avg_sq"} and float(v["step"]) == 5 for v in st.values())
         mine2 = FusedAdam(groups(my_p), **kw)
-        mine2.load_state_dict(ref.state_dict())
+        # (deepcopy: state_dict() hands out the live 'step' tensors and load_state_dict keeps them, as torch's own does)
+        mine2.load_state_dict(copy.deepcopy(ref.state_dict()))
         for a, b in zip(ref_p, my_p):
             gr = torch.randn(a.shape, generator=g).to(DEV)
             a.grad, b.grad = gr.clone(), gr.clone()

@@ -10,8 +10,8 @@
 //       box {32 px, 32 channels, 1 image, 4 pixel groups} lands a 128-pixel x 32-channel tile (SWIZZLE_128B_BASE32B).
 //       Four "split" warps then rewrite it in place as hi and write lo to a second buffer.
 //   B = class table [C][D] (K-major), pre-split into hi / lo, zero-padded to [Cpad][Dpad], by szn_embed_argmax.
-//   D = three accumulators in TMEM (hh, lh, hl: independent MMA chains), summed by the epilogue, which scales by
-//       1/|e_c|, takes the first maximum over c < C and writes the int64 label.
+//   D = three accumulators in TMEM (hh, lh, hl: independent MMA chains; for 128 < C <= 256 two: hh and hl + lh),
+//       summed by the epilogue, which scales by 1/|e_c|, takes the first maximum over c < C and writes the int64 label.
 // Warp roles: 0 TMA producer, 1 MMA issuer, 2-5 operand split, 6-9 epilogue.  Persistent over 128-pixel tiles.
 #include "szn_internal.h"
 #include "szn_ptx.cuh"
@@ -21,7 +21,7 @@ namespace szn {
 struct ArgmaxParams {
   int D, C, Cpad, B;
   long long hw;
-  int tiles_per_img, total_tiles, kchunks, stages, acc_cols, nbuf;
+  int tiles_per_img, total_tiles, kchunks, stages, acc_cols, nbuf, nacc;
   const float* inv_en;  // [Cpad] 1 / |e_c| (1 for zero rows)
   long long* labels;
 };
@@ -93,7 +93,7 @@ embed_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tptr;
-  const uint32_t buf_cols = 3u * (uint32_t)p.acc_cols;  // hh | lh | hl
+  const uint32_t buf_cols = (uint32_t)(p.nacc * p.acc_cols);  // hh | hl | lh, or (Cpad = 256) hh | hl + lh
 
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
@@ -141,9 +141,16 @@ embed_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_con
           const uint32_t acc = (uint32_t)((kc | k) != 0);
           // B_hi and B_lo are stacked along N, so A_hi x [B_hi; B_lo] yields the hi*hi and hi*lo partial sums with ONE
           // instruction (an N <= 256 MMA costs about the same ~130 cycles whatever N is); lo*hi is the second one.
-          tc_mma<true>(d0, ah, bh, idesc2, acc);                              // columns [0, 2*Cpad): hh | hl
-          tc_mma<true>(d0 + 2u * (uint32_t)p.acc_cols, al, bh, idesc, acc);  // columns [2*Cpad, 3*Cpad): lh
-          (void)bl;
+          if (p.nacc == 3) {
+            tc_mma<true>(d0, ah, bh, idesc2, acc);                              // columns [0, 2*Cpad): hh | hl
+            tc_mma<true>(d0 + 2u * (uint32_t)p.acc_cols, al, bh, idesc, acc);  // columns [2*Cpad, 3*Cpad): lh
+          } else {
+            // Cpad = 256: three accumulators would need 768 TMEM columns.  The two small terms only ever appear as
+            // their sum, so hi*lo and lo*hi share the second accumulator: 2 x 256 = all 512 columns.
+            tc_mma<true>(d0, ah, bh, idesc, acc);                               // columns [0, 256): hh
+            tc_mma<true>(d0 + (uint32_t)p.acc_cols, ah, bl, idesc, acc);       // columns [256, 512): hl
+            tc_mma<true>(d0 + (uint32_t)p.acc_cols, al, bh, idesc, 1u);        //                   += lh
+          }
         }
         tc_commit(&empty[s]);
         if (++s == stages) s = 0, ph ^= 1u;
@@ -204,10 +211,12 @@ embed_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_con
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
-        tmem_ld32(tbase + (uint32_t)(2 * p.acc_cols + c0), v);
-        tmem_ld_wait();
+        if (p.nacc == 3) {
+          tmem_ld32(tbase + (uint32_t)(2 * p.acc_cols + c0), v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+        }
         if (c0 + 32 >= p.Cpad) {  // last TMEM read of the tile
           tc_fence_before();
           __syncwarp();
@@ -277,8 +286,8 @@ int embed_argmax_tc(const float* score, const float* table, int n, int D, long l
   p.total_tiles = p.tiles_per_img * n;
   p.kchunks = Dpad / 32;
   p.acc_cols = Cpad;
-  p.nbuf = (2 * 3 * Cpad <= 512) ? 2 : 1;
-  if (3 * Cpad > 512) return 1;  // Cpad = 256 needs a 2-accumulator variant: CUDA-core fallback for now
+  p.nacc = Cpad == 256 ? 2 : 3;  // Cpad = 256: hi*lo and lo*hi share one accumulator (2 x 256 = 512 TMEM columns)
+  p.nbuf = (2 * p.nacc * Cpad <= 512) ? 2 : 1;
   const int stage_bytes = 2 * 128 * 128 + 2 * Cpad * 128;
   int stages = (227 * 1024 - 1024 - 512) / stage_bytes;
   if (stages > 8) stages = 8;
