@@ -1,0 +1,226 @@
+"""Parity at BASELINE.json's FULL sizes (configs[1]: B=8, 3x512x512, D=300, C=59, TF32) through size-independent
+properties, because the CPU oracle needs minutes there:
+
+* the trilinear identity that ties the three conv kernels together, <conv(x,w), dy> = <x, dgrad(dy,w)> = <w, wgrad(x,dy)>,
+  on the real layer shapes (conv1_2, conv3_2, conv5_1, fc6 incl. col2im, fc7);
+* adjointness of the x32 upsample + crop pair; scale / class-permutation invariance of the nearest-embedding labels and a
+  crop of them against the oracle; additivity over images, orthogonality (dL/ds . s = 0), ignore-mask and linearity of the
+  cosine-loss gradient; one image of the loss against the oracle;
+* batch consistency of the whole model: image b of a B=8 forward equals the B=1 forward of that image.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import szn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+B, H, W, D, C = 8, 512, 512, 300, 59
+
+
+def L():
+    from zeroshotsemanticsegmentation_b200 import _lib
+    return _lib
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def round_tf32(t):
+    i = t.contiguous().view(torch.int32)
+    i = ((i + 0xFFF + ((i >> 13) & 1)) >> 13) << 13
+    return i.view(torch.float32)
+
+
+def dot(a, b):
+    return float((a.double() * b.double()).sum().item())
+
+
+LAYERS = [  # name, H, W, Cin, Cout, k, pad  (feature-map sizes of a 512x512 image)
+    ("conv1_2", 710, 710, 64, 64, 3, 1),
+    ("conv3_2", 178, 178, 256, 256, 3, 1),
+    ("conv5_1", 45, 45, 512, 512, 3, 1),
+    ("fc6", 23, 23, 512, 4096, 7, 0),
+    ("fc7", 17, 17, 4096, 4096, 1, 0),
+]
+
+
+@pytest.mark.parametrize("layer", LAYERS, ids=[l[0] for l in LAYERS])
+def test_conv_trilinear_identity_full_size(layer):
+    name, h, w, cin, cout, k, pad = layer
+    lib = L()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = round_tf32(torch.randn(B, h, w, cin, device=DEV, generator=g))                       # NHWC
+    wt = round_tf32(torch.randn(cout, cin, k, k, device=DEV, generator=g) / (cin * k * k) ** 0.5)  # OIHW
+    ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    wf = torch.empty((cout, k * k, cin), device=DEV)
+    lib.call("szn_pack_weight", 0, wt.data_ptr(), wf.data_ptr(), cout, cin, k, k, cout, st())
+    y = torch.full((B, ho, wo, cout), float("nan"), device=DEV)
+    zero_bias = torch.zeros(cout, device=DEV)
+    lib.call("szn_conv_fwd", 0, x.data_ptr(), wf.data_ptr(), zero_bias.data_ptr(), y.data_ptr(), B, h, w, cin, cout, k, k,
+             pad, 0, None, 0, 0, cout, st())  # production epilogue: y stored rounded to TF32
+    assert torch.isfinite(y).all()
+    # an upstream gradient correlated with y, so that the inner products are large compared with their rounding noise
+    dy = round_tf32(0.5 * y + 0.1 * y.std() * torch.randn(y.shape, device=DEV, generator=g))
+    dx = torch.full((B, h, w, cin), float("nan"), device=DEV)
+    if k >= 5:  # fc6: one GEMM against the (tap, ci)-major weights + col2im, as engine.py runs it
+        wd = torch.empty((cin, k * k, cout), device=DEV)
+        lib.call("szn_pack_weight_dgrad", 0, wt.data_ptr(), wd.data_ptr(), cout, cin, k, k, cout, 1, st())
+        dcol = torch.empty((B, ho, wo, k * k * cin), device=DEV)
+        lib.call("szn_conv_dgrad", 0, dy.data_ptr(), wd.data_ptr(), dcol.data_ptr(), B, ho, wo, k * k * cin, cout, 1, 1, 0,
+                 None, None, 0, cout, None, st())
+        lib.call("szn_col2im", 0, dcol.data_ptr(), dx.data_ptr(), B, h, w, cin, k, k, st())
+    else:
+        wd = torch.empty((cin, k * k, cout), device=DEV)
+        lib.call("szn_pack_weight_dgrad", 0, wt.data_ptr(), wd.data_ptr(), cout, cin, k, k, cout, 0, st())
+        lib.call("szn_conv_dgrad", 0, dy.data_ptr(), wd.data_ptr(), dx.data_ptr(), B, h, w, cin, cout, k, k, pad,
+                 None, None, 0, cout, None, st())
+    dw = torch.zeros((cout, k * k * cin), device=DEV)
+    lib.call("szn_conv_wgrad", 0, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), B, h, w, cin, cout, k, k, pad, cout, st())
+    torch.cuda.synchronize()
+    assert torch.isfinite(dx).all() and torch.isfinite(dw).all()
+    i_fwd = dot(y, dy)
+    i_dgrad = dot(x, dx)
+    i_wgrad = dot(wt.permute(0, 2, 3, 1).reshape(cout, k * k * cin), dw)
+    print(name, "<y,dy> %.9e  <x,dx> %.9e  <w,dw> %.9e" % (i_fwd, i_dgrad, i_wgrad))
+    assert i_fwd > 0
+    # y and dx are stored rounded to TF32 (2^-11 per element, random sign), dw is fp32: the three agree to ~1e-6
+    assert abs(i_dgrad - i_fwd) < 1e-4 * i_fwd
+    assert abs(i_wgrad - i_fwd) < 1e-4 * i_fwd
+    assert abs(i_wgrad - i_dgrad) < 1e-4 * i_fwd
+    # a checksum of checksums: the bias-gradient column sums fused into the dgrad epilogue equal the sums of the stored dx
+    if k < 5:
+        colsum = torch.zeros(cin, device=DEV)
+        dx2 = torch.empty_like(dx)
+        lib.call("szn_conv_dgrad", 0, dy.data_ptr(), wd.data_ptr(), dx2.data_ptr(), B, h, w, cin, cout, k, k, pad,
+                 None, None, 0, cout, colsum.data_ptr(), st())
+        torch.cuda.synchronize()
+        assert torch.equal(dx2, dx)  # deterministic
+        want = dx.double().sum(dim=(0, 1, 2))
+        assert float((colsum.double() - want).abs().max()) < 1e-4 * float(want.abs().max()) + 1e-3
+
+
+@pytest.fixture(scope="module")
+def head():
+    """score = upsample(s17) at full size, labels, table, targets: shared by the head tests."""
+    import zeroshotsemanticsegmentation_b200 as szn
+    lib = L()
+    g = torch.Generator(device=DEV).manual_seed(9)
+    Dp = 320
+    s17 = torch.randn(B, 17, 17, Dp, device=DEV, generator=g)
+    f = torch.full((B, D, H, W), float("nan"), device=DEV)
+    lib.call("szn_upsample32_crop_fwd", s17.data_ptr(), f.data_ptr(), B, D, H, W, 17, 17, Dp, 0, st())
+    _, lab, table = O.synth_batch(B, H, W, C, D, seed=1337)
+    torch.cuda.synchronize()
+    assert torch.isfinite(f).all()
+    return dict(s17=s17, f=f, lab=lab.to(DEV), table=table.to(DEV), U=szn.utils, Dp=Dp)
+
+
+def test_upsample_pair_is_adjoint_full_size(head):
+    lib = L()
+    f, s17, Dp = head["f"], head["s17"], head["Dp"]
+    g = torch.Generator(device=DEV).manual_seed(10)
+    gy = 0.5 * f + 0.1 * torch.randn(f.shape, device=DEV, generator=g)
+    ds = torch.zeros(B, 17, 17, Dp, device=DEV)
+    lib.call("szn_upsample32_crop_bwd", 0, gy.data_ptr(), ds.data_ptr(), B, D, H, W, 17, 17, Dp, 0, st())
+    torch.cuda.synchronize()
+    a, b = dot(f, gy), dot(s17[..., :D], ds[..., :D])
+    print("<U s, g> %.9e  <s, U^T g> %.9e" % (a, b))
+    assert a > 0 and abs(a - b) < 1e-4 * a        # ds is stored rounded to TF32
+    assert float(ds[..., D:].abs().max()) == 0.0  # channels of the other head are not touched
+    # the bilinear taps of one output pixel sum to 1 away from the map border: a constant map stays constant there
+    ones = torch.ones(1, 17, 17, Dp, device=DEV)
+    out = torch.empty(1, D, H, W, device=DEV)
+    lib.call("szn_upsample32_crop_fwd", ones.data_ptr(), out.data_ptr(), 1, D, H, W, 17, 17, Dp, 0, st())
+    torch.cuda.synchronize()
+    inner = out[:, :, 13:H - 45, 13:W - 45]  # rows whose two source rows both exist (crop 19, kernel 64, stride 32)
+    assert float((inner - 1).abs().max()) < 1e-6
+
+
+def test_labels_invariances_and_crop_vs_oracle_full_size(head):
+    U, f, table = head["U"], head["f"], head["table"]
+    lbl = U.infer_lbl_device(f, table)
+    assert lbl.shape == (B, H, W) and lbl.dtype == torch.int64 and int(lbl.min()) >= 0 and int(lbl.max()) < C
+    # positive power-of-two scaling of the scores is exact in fp32: labels are bit-identical
+    assert torch.equal(U.infer_lbl_device(f * 4.0, table), lbl)
+    # class permutation: the arithmetic per (pixel, class) does not depend on the row's position in the table
+    perm = torch.randperm(C, generator=torch.Generator().manual_seed(1)).to(DEV)
+    lbl_p = U.infer_lbl_device(f, table[perm])
+    mism = perm[lbl_p] != lbl
+    print("label mismatches under class permutation:", int(mism.sum()))
+    assert float(mism.float().mean()) < 1e-6  # only exact ties (lowest index wins) may move
+    # a 64x64 crop of image 5 against the oracle (exact away from the oracle's own numerical near-ties)
+    crop = f[5:6, :, 100:164, 200:264].cpu()
+    ref = O.infer_lbl(crop, table.cpu())
+    got = lbl[5:6, 100:164, 200:264].cpu().numpy()
+    bad = got != ref
+    if bad.any():
+        sn = crop / crop.norm(dim=1, keepdim=True)
+        tn = table.cpu() / table.cpu().norm(dim=1, keepdim=True)
+        top2 = torch.einsum("ndhw,cd->nchw", sn, tn).topk(2, dim=1).values
+        assert ((top2[:, 0] - top2[:, 1]).numpy()[bad] < 1e-5).all()
+    assert bad.mean() < 1e-3
+
+
+def test_cosine_loss_properties_full_size(head):
+    U, f, lab, table = head["U"], head["f"], head["lab"], head["table"]
+    s = f.clone().requires_grad_(True)
+    loss = U.cosine_loss(s, lab, table=table)
+    (g1,) = torch.autograd.grad(loss, s, retain_graph=True)
+    (g2,) = torch.autograd.grad(loss * 2.0, s)
+    assert 0.0 <= loss.item() <= 2.0
+    assert torch.equal(g2, g1 * 2.0)                       # linear in the upstream gradient (power of two: exact)
+    ign = (lab < 0)[:, None].expand_as(g1)
+    assert float(g1[ign].abs().max()) == 0.0               # ignored pixels (label -1) get no gradient
+    # d cos(s, e) / d s is orthogonal to s at every pixel
+    num = (g1.double() * f.double()).sum(1).abs()
+    den = g1.double().norm(dim=1) * f.double().norm(dim=1) + 1e-300
+    assert float((num / den).max()) < 1e-4
+    # additivity over images: N * loss = sum_b N_b * loss_b
+    nb = (lab >= 0).flatten(1).sum(1).double()
+    per = torch.stack([U.cosine_loss(f[b:b + 1], lab[b:b + 1], table=table).double() for b in range(B)])
+    assert abs(float((per * nb).sum() / nb.sum()) - loss.item()) < 2e-6
+    # one image against the oracle (the reference's formula, utils.py:75-102)
+    fb, lb = f[2:3].cpu(), lab[2:3].cpu()
+    ref = O.cosine_loss(fb, lb, O.target_embed_from_labels(lb, table.cpu())).item()
+    assert abs(float(per[2]) - ref) < 1e-5
+    # the MSE loss at full size against the same image
+    ref_mse = O.mse_loss(fb, lb, O.target_embed_from_labels(lb, table.cpu())).item()
+    got_mse = U.mse_loss(f[2:3], lab[2:3], table=table).item()
+    assert abs(got_mse - ref_mse) < 1e-5 * max(1.0, abs(ref_mse))
+
+
+def test_model_batch_consistency_full_size():
+    """Image 3 of a B=8 step equals the B=1 run of that image (forward, both heads, labels)."""
+    import zeroshotsemanticsegmentation_b200 as szn
+    from zeroshotsemanticsegmentation_b200 import synth
+    U = szn.utils
+    m = synth.init_model_(szn.FCN32s(D), seed=1337).to(DEV).eval()
+    x, lab, table = synth.synth_batch(B, H, W, C, D, seed=1337)
+    x, table = x.to(DEV), table.to(DEV)
+    with torch.no_grad():
+        f8, s8 = m(x, mode="both")
+        f1, s1 = m(x[3:4].contiguous(), mode="both")
+    assert f8.shape == (B, D, H, W) and s8.shape == (B, 2, H, W) and torch.isfinite(f8).all()
+    ef = float((f8[3:4] - f1).abs().max() / f1.abs().max())
+    es = float((s8[3:4] - s1).abs().max() / s1.abs().max())
+    print("B=8 vs B=1 forward: rel diff f %.3e  s %.3e  (bit-identical: %s)" % (ef, es, torch.equal(f8[3:4], f1)))
+    # other batch sizes may pick other tile shapes, i.e. another fp32 summation order, and a last-bit difference can move
+    # a TF32 rounding of a stored activation: equal within the forward tolerance of the north star, not bit for bit
+    assert ef < 1e-3 and es < 1e-3
+    l8 = U.infer_lbl_device(f8, table)[3]
+    l1 = U.infer_lbl_device(f1, table)[0]
+    assert float((l8 != l1).float().mean()) < 1e-3
+    # whole training step at full size: finite loss and gradients, frozen upscore untouched
+    m.train()
+    f = m(x, mode="fcn")
+    loss = U.cosine_loss(f, lab.to(DEV), table=table)
+    loss.backward()
+    assert np.isfinite(loss.item())
+    for n, p in m.named_parameters():
+        if "upscore" in n or n.startswith("seenmask"):
+            assert p.grad is None, n
+        else:
+            assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0, n
