@@ -119,7 +119,7 @@ int szn_loss_finalize(int kind, const double* accum, float* loss, void* stream);
 
 /* ---- inference (utils.py:159-205) ---- */
 /* infer_lbl: labels = argmax_c <s_p,e_c>/(|s_p| |e_c|), |e_c|==0 -> 1, lowest index on ties.
- * Runs as an error-compensated (3xTF32) tcgen05 GEMM when h*w % 32 == 0 and C <= 128, else on CUDA cores (fp32 FMA).
+ * Runs as an error-compensated (3xTF32) tcgen05 GEMM when h*w % 32 == 0 and C <= 256, else on CUDA cores (fp32 FMA).
  * en_scratch: szn_embed_argmax_scratch_floats(C, D) floats of device memory. */
 long long szn_embed_argmax_scratch_floats(int C, int D);
 int szn_embed_argmax(const float* score, const float* table, int n, int D, int h, int w, int C, float* en_scratch,

@@ -197,3 +197,67 @@ def test_seenmask_phase_matches_oracle_and_torch_adam(tmp_path):
     best = torch.load(os.path.join(str(tmp_path), "best"), weights_only=False)
     assert best["epoch"] == 7 and torch.equal(best["model_state_dict"]["seenmask_score.weight"].cpu(),
                                               sd["seenmask_score.weight"].cpu())
+
+
+class _FakeReducer:
+    """Stands in for ddp.GradientAllReduce on one GPU: behaves as if a second rank had contributed the same
+    {sum, n_valid} to the loss accumulator."""
+
+    def __init__(self):
+        self.seen = []
+
+    def accum_hook(self, accum):
+        self.seen.append(accum.clone())
+        accum.mul_(2.0)
+
+
+def test_cross_entropy_accum_hook_uses_the_global_count():
+    """utils.py:46-47 under data parallelism: the mean divides by the valid pixels of ALL ranks."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    g = torch.Generator().manual_seed(4)
+    score = torch.randn(2, 5, 9, 11, generator=g).to(DEV)
+    tgt = torch.randint(-1, 5, (2, 9, 11), generator=g).to(DEV)
+    n_valid = int((tgt >= 0).sum())
+    for size_average in (True, False):
+        s0 = score.clone().requires_grad_(True)
+        base = U.cross_entropy2d(s0, tgt, size_average=size_average)
+        base.backward()
+        red = _FakeReducer()
+        s1 = score.clone().requires_grad_(True)
+        loss = U.cross_entropy2d(s1, tgt, size_average=size_average, accum_hook=red.accum_hook)
+        loss.backward()
+        acc = red.seen[0].cpu()
+        assert int(acc[1]) == n_valid
+        if size_average:
+            assert abs(float(acc[0]) / n_valid - base.item()) < 1e-5
+            assert abs(loss.item() - base.item()) < 1e-6          # 2*sum / 2*N
+            assert torch.allclose(s1.grad, s0.grad * 0.5, rtol=1e-6, atol=1e-12)   # each rank's share of the global mean
+        else:
+            assert abs(loss.item() - 2 * base.item()) < 1e-4 * abs(base.item())  # the global sum
+            assert torch.allclose(s1.grad, s0.grad, rtol=1e-6, atol=1e-12)       # a sum's gradient does not depend on N
+
+
+def test_trainers_hand_the_reducer_hook_to_their_losses(tmp_path):
+    from zeroshotsemanticsegmentation_b200 import trainer as T
+    from zeroshotsemanticsegmentation_b200.optim import FusedAdam
+    m, _ = build_model(14)
+    batch = T.collate_padded([sample(40, 56, 9)])
+    red = _FakeReducer()
+    tr = fcn_trainer(m, Loader([batch]), Loader([batch]), None, reducer=red)
+    _, loss, _, _ = tr.forward(*batch)
+    tr0 = fcn_trainer(m, Loader([batch]), Loader([batch]), None)
+    _, loss0, _, _ = tr0.forward(*batch)
+    assert len(red.seen) == 1 and int(red.seen[0][1]) == int((batch[1] >= 0).sum())
+    assert abs(loss.item() - loss0.item()) < 1e-6  # (2N - 2*sum) / 2N
+    head = T.freeze_for_seenmask(m)
+    sm = T.SeenmaskTrainer(True, m, FusedAdam([{"params": head}], lr=1e-3), Loader([batch]), Loader([batch]), None, "pascal",
+                           1, None, unseen=UNSEEN, reducer=red)
+    _, l1, _, _ = sm.forward(*batch)
+    l1.backward()
+    g1 = m.seenmask_score.weight.grad.clone()
+    m.zero_grad()
+    sm.reducer, sm._accum_hook = None, None
+    _, l0, _, _ = sm.forward(*batch)
+    l0.backward()
+    assert len(red.seen) == 2 and abs(l1.item() - l0.item()) < 1e-6
+    assert torch.allclose(g1, m.seenmask_score.weight.grad * 0.5, rtol=1e-4, atol=1e-10)

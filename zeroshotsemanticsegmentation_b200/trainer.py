@@ -16,6 +16,9 @@ the per-iteration work runs:
 * any batch size works (the reference's losses are only correct for n == 1): ``collate_padded`` batches variable-size
   images by padding images with 0 (the mean pixel after ``transform``) and labels with the ignore label -1.
 
+* ``reducer=ddp.GradientAllReduce(model)`` makes a trainer data-parallel (one process per GPU over its own shard of the
+  loader): gradients are summed over ranks inside backward and every loss divides by the GLOBAL valid-pixel count.
+
 Out of scope: tensorboard images, segmentation visualisations, US/Eastern timestamps; ``tb_writer`` may be
 ``None`` or anything with ``add_scalar``; ``visualize`` is an optional callback.  There is no CPU path: ``cuda=False`` raises.
 """
@@ -98,7 +101,8 @@ class _Base(object):
     log_prefix = ""
     tb_prefix = "fcn"
 
-    def _setup(self, cuda, model, optimizer, train_loader, val_loader, log_dir, dataset, max_epoch, tb_writer, n_class):
+    def _setup(self, cuda, model, optimizer, train_loader, val_loader, log_dir, dataset, max_epoch, tb_writer, n_class,
+               reducer=None):
         if not cuda:
             raise RuntimeError("the B200 trainers run on CUDA only (no CPU fallback): pass cuda=True")
         self.cuda = cuda
@@ -121,6 +125,10 @@ class _Base(object):
         if self.device.type != "cuda":
             raise RuntimeError("move the model to the GPU before building a trainer (train.py:121-122)")
         self.verbose = True
+        # data parallel (one process per GPU, ddp.GradientAllReduce attached to the model): the losses then normalise by
+        # the valid-pixel count of the GLOBAL batch; gradients are all-reduced inside backward
+        self.reducer = reducer
+        self._accum_hook = reducer.accum_hook if reducer is not None else None
         if log_dir:
             os.makedirs(log_dir, exist_ok=True)
 
@@ -208,13 +216,14 @@ class Trainer(_Base):
 
     def __init__(self, cuda, model, optimizer, train_loader, val_loader, log_dir, dataset, max_epoch, tb_writer=None,
                  pixel_embeddings=None, loss_func=None, unseen=None, val_unseen=None, label_names=None, forced_unseen=False,
-                 embed_arr=None, n_class=None, visualize=None):
+                 embed_arr=None, n_class=None, visualize=None, reducer=None):
         if pixel_embeddings and embed_arr is None:
             # each embedding has norm between 0 and 1 (trainer_fcn.py:47-49); path relative to the reference root
             embed_arr = utils.load_obj("datasets/%s/embeddings/norm_embed_arr_%s" % (dataset, str(pixel_embeddings)))
         if n_class is None and embed_arr is not None and not hasattr(getattr(train_loader, "dataset", None), "class_names"):
             n_class = int(np.asarray(embed_arr).shape[0])
-        self._setup(cuda, model, optimizer, train_loader, val_loader, log_dir, dataset, max_epoch, tb_writer, n_class)
+        self._setup(cuda, model, optimizer, train_loader, val_loader, log_dir, dataset, max_epoch, tb_writer, n_class,
+                    reducer)
         self.pixel_embeddings = pixel_embeddings
         self.loss_func = loss_func
         self.unseen = list(unseen) if unseen else []  # all unseen classes (train_unseen + val_unseen)
@@ -244,11 +253,12 @@ class Trainer(_Base):
 
     # ---- the hot path, in the reference's call order (trainer_fcn.py:83-120) ----
     def _loss(self, score, target, target_embed):
+        table = None if target_embed is not None else self.embeddings
         if self.loss_func == "cos":
-            return utils.cosine_loss(score, target, target_embed, table=None if target_embed is not None else self.embeddings)
+            return utils.cosine_loss(score, target, target_embed, table=table, accum_hook=self._accum_hook)
         if self.loss_func == "mse":
-            return utils.mse_loss(score, target, target_embed, table=None if target_embed is not None else self.embeddings)
-        return utils.cross_entropy2d(score, target, size_average=False)
+            return utils.mse_loss(score, target, target_embed, table=table, accum_hook=self._accum_hook)
+        return utils.cross_entropy2d(score, target, size_average=False, accum_hook=self._accum_hook)
 
     def _forward_device(self, data, target, szn=False):
         target, target_embed = self._split_target(target)
@@ -337,8 +347,9 @@ class SeenmaskTrainer(_Base):
     tb_prefix = "seenmask"
 
     def __init__(self, cuda, model, optimizer, train_loader, val_loader, log_dir, dataset, max_epoch, tb_writer=None,
-                 checkpoint=None, unseen=None, n_class=None, visualize=None):
-        self._setup(cuda, model, optimizer, train_loader, val_loader, log_dir, dataset, max_epoch, tb_writer, n_class)
+                 checkpoint=None, unseen=None, n_class=None, visualize=None, reducer=None):
+        self._setup(cuda, model, optimizer, train_loader, val_loader, log_dir, dataset, max_epoch, tb_writer, n_class,
+                    reducer)
         self.checkpoint = checkpoint if checkpoint is not None else {}
         self.unseen = list(unseen) if unseen else []
         self.visualize = visualize
@@ -352,7 +363,7 @@ class SeenmaskTrainer(_Base):
         data, target = self._to_device(data), self._to_device(target)
         target = utils.seenmask_target(target, self.unseen, self.n_class)  # trainer_seenmask.py:53-58, on the device
         score = self.model(data, mode="seenmask")                           # :64
-        loss = utils.cross_entropy2d(score, target, size_average=True)      # :65
+        loss = utils.cross_entropy2d(score, target, size_average=True, accum_hook=self._accum_hook)  # :65
         lbl_pred = score.detach().max(1)[1]                                  # :67
         return score, loss, lbl_pred, target
 

@@ -101,7 +101,7 @@ class _EmbedLoss(torch.autograd.Function):
 
 class _CrossEntropy2d(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, score, target, size_average):
+    def forward(ctx, score, target, size_average, accum_hook):
         _check_cuda(score, target)
         n, c, h, w = score.shape
         sc = _as_f32(score)
@@ -110,8 +110,11 @@ class _CrossEntropy2d(torch.autograd.Function):
         lse = torch.empty((n * h * w,), device=dev, dtype=torch.float32)
         accum = torch.empty(2, device=dev, dtype=torch.float64)
         loss = torch.empty((), device=dev, dtype=torch.float32)
-        call("szn_ce2d_fwd", ptr(sc), ptr(tg), n, c, h, w, int(bool(size_average)), ptr(lse), ptr(accum), ptr(loss),
-             _lib.stream())
+        st = _lib.stream()
+        call("szn_ce2d_fwd", ptr(sc), ptr(tg), n, c, h, w, int(bool(size_average)), ptr(lse), ptr(accum), ptr(loss), st)
+        if accum_hook is not None:  # data parallel: {sum, n_valid} over ALL ranks (the mean divides by the global count)
+            accum_hook(accum)
+            call("szn_loss_finalize", 3 if size_average else 2, ptr(accum), ptr(loss), st)
         ctx.saved = (sc, tg, lse, accum, int(bool(size_average)))
         return loss
 
@@ -122,15 +125,15 @@ class _CrossEntropy2d(torch.autograd.Function):
         g = torch.empty_like(sc)
         go = gout.detach().contiguous().float()
         call("szn_ce2d_bwd", ptr(sc), ptr(tg), n, c, h, w, sa, ptr(lse), ptr(accum), ptr(go), ptr(g), _lib.stream())
-        return g, None, None
+        return g, None, None, None
 
 
-def cross_entropy2d(score, target, weight=None, size_average=False):
+def cross_entropy2d(score, target, weight=None, size_average=False, accum_hook=None):
     """Per-pixel softmax cross entropy, summed over ``target >= 0`` (``utils.py:19-48``).
     score (n,c,h,w), target (n,h,w) int64; ``size_average`` divides by the number of valid pixels."""
     if weight is not None:
         raise NotImplementedError("class weights are never passed by the reference trainers")
-    return _CrossEntropy2d.apply(score, target, size_average)
+    return _CrossEntropy2d.apply(score, target, size_average, accum_hook)
 
 
 def mse_loss(score, target, target_embed=None, table=None, accum_hook=None):
