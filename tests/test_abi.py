@@ -130,3 +130,40 @@ def test_missing_extension_fails_loudly():
     env = dict(os.environ, SZN_LIB="/nonexistent/libszn.so")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert "RAISED True" in out.stdout, out.stdout + out.stderr
+
+
+def _c_prototypes():
+    """name -> list of C parameter type strings, parsed from include/szn.h."""
+    src = open(os.path.join(ROOT, "include", "szn.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for ret, name, params in re.findall(r"\b(int|long long|const char\*)\s+(szn_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        params = params.strip()
+        types = []
+        if params and params != "void":
+            for p in params.split(","):
+                p = " ".join(p.split())
+                types.append(p.rsplit(" ", 1)[0] if not p.endswith("*") else p)  # drop the parameter name
+        protos[name] = (ret, types)
+    return protos
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every argtypes list of the ctypes binding has the arity and the scalar widths of the C prototype it binds
+    (a mismatch would corrupt arguments silently: ctypes cannot check it at run time)."""
+    import ctypes
+    from zeroshotsemanticsegmentation_b200 import _lib
+    protos = _c_prototypes()
+
+    def expected(ctype):
+        if "*" in ctype:
+            return ctypes.c_void_p
+        return {"int": ctypes.c_int, "long long": ctypes.c_longlong, "unsigned long long": ctypes.c_ulonglong,
+                "float": ctypes.c_float}[ctype]
+
+    assert set(_lib.SIGNATURES) <= set(protos)
+    for name, argtypes in _lib.SIGNATURES.items():
+        ret, ctypes_c = protos[name]
+        assert ret == "int", name
+        want = [expected(t) for t in ctypes_c]
+        assert list(argtypes) == want, "%s: binding %s vs header %s" % (name, argtypes, ctypes_c)

@@ -234,7 +234,7 @@ def test_model_full_size_forward_vs_oracle_and_batch_consistency():
     l1 = U.infer_lbl_device(f1, table)[0].cpu().numpy()
     agree8, agree1 = float((l8 == l_ref[0]).mean()), float((l1 == l_ref[0]).mean())
     print("end-to-end label agreement with the oracle: B=8 %.5f  B=1 %.5f" % (agree8, agree1))
-    assert agree8 > 0.9 and agree1 > 0.9  # a random-init net has many near-ties; the golden cases hold > 0.99
+    assert agree8 > 0.99 and agree1 > 0.99  # measured 0.9997
     # whole training step at full size: finite loss and gradients, frozen upscore untouched
     m.train()
     f = m(x, mode="fcn")

@@ -262,19 +262,22 @@ class FCN32sFunction(torch.autograd.Function):
 
         # ---------------- score heads: wgrad / bias / dgrad ----------------
         rows17 = B * hs * ws
-        if any(need[k] for k in ("score_fr.weight", "seenmask_score.weight")):
+        # a head whose output received no gradient (mode='fcn' / 'seenmask') gets None, as autograd gives the reference,
+        # not zeros: an optimizer with momentum / weight decay would otherwise move parameters that were not used
+        want = {"score_fr": gf is not None, "seenmask_score": gs is not None}
+        if any(need[k + ".weight"] and want[k] for k in want):
             dwh = zeros((Dp, 4096))
             call("szn_conv_wgrad", dt, ptr(sv["h7"]), ptr(ds17), ptr(dwh), B, hs, ws, 4096, Dp, 1, 1, 0, Dp, st)
-            if need["score_fr.weight"]:
+            if need["score_fr.weight"] and want["score_fr"]:
                 grads["score_fr.weight"] = dwh[:D].reshape(D, 4096, 1, 1)
-            if need["seenmask_score.weight"]:
+            if need["seenmask_score.weight"] and want["seenmask_score"]:
                 grads["seenmask_score.weight"] = dwh[D:D + 2].reshape(2, 4096, 1, 1)
-        if any(need[k] for k in ("score_fr.bias", "seenmask_score.bias")):
+        if any(need[k + ".bias"] and want[k] for k in want):
             dbh = zeros((Dp,))
             call("szn_bias_grad", dt, ptr(ds17), ptr(dbh), rows17, Dp, Dp, st)
-            if need["score_fr.bias"]:
+            if need["score_fr.bias"] and want["score_fr"]:
                 grads["score_fr.bias"] = dbh[:D]
-            if need["seenmask_score.bias"]:
+            if need["seenmask_score.bias"] and want["seenmask_score"]:
                 grads["seenmask_score.bias"] = dbh[D:D + 2]
         if first_needed is None:
             return _finish(module, grads)
