@@ -1,0 +1,113 @@
+// Micro-benchmark (round-2 tool, NOT part of libszn.so): cycles per tcgen05.mma as a function of M, N, kind and the
+// number of TMEM accumulators the K-steps rotate over.  It answers the question DESIGN.md §4.1 leaves open for the
+// narrow layers (conv1_2: N = 64, conv2_x: N = 128): is a ~130-cycle floor per instruction real, and would M = 64 x N = 256
+// (weights as the A operand, pixels as B) do twice the work per instruction?
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/probe_mma tools/probe_mma.cu
+//   ./tools/probe_mma            (on the GPU box; prints one line per configuration)
+//
+// One CTA per SM (148), one thread issues `iters` MMAs (K-major SWIZZLE_128B operands resident in shared memory, zero
+// filled: the tensor pipe does not care about values), rotating over `nacc` accumulators, then commits and waits.
+// cycles/MMA = (clock64 after the commit's mbarrier flips - clock64 before the first issue) / iters.
+#include <cstdio>
+#include <cstdlib>
+
+#include "../zeroshotsemanticsegmentation_b200/csrc/szn_ptx.cuh"
+
+using namespace szn;
+
+struct Cfg {
+  int tf32, M, N, nacc, iters;
+};
+
+__global__ void __launch_bounds__(128, 1) probe_kernel(Cfg c, long long* cycles_out) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t a0 = smem_u32(raw);
+  uint8_t* smem = raw + ((1024u - (a0 & 1023u)) & 1023u);
+  // A: up to 128 rows x 128 B, B: up to 256 rows x 128 B, 4 stages each so that consecutive MMAs read other addresses
+  constexpr int A_BYTES = 128 * 128, B_BYTES = 256 * 128, STAGES = 4;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < STAGES * (A_BYTES + B_BYTES) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 32) {
+    tmem_alloc(tptr, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc(c.tf32 ? 2 : 1, 0, 0, c.M, c.N);
+    const uint32_t a_base = smem_u32(smem), b_base = a_base + STAGES * A_BYTES;
+    const int acc_cols = c.N < 32 ? 32 : c.N;
+    const long long t0 = clock64();
+    for (int it = 0; it < c.iters; ++it) {
+      const int s = it & (STAGES - 1), k = (it >> 2) & 3, acc = it % c.nacc;
+      const uint64_t ad = umma_desc_sw128(a_base + s * A_BYTES + k * 32, 16, 1024);
+      const uint64_t bd = umma_desc_sw128(b_base + s * B_BYTES + k * 32, 16, 1024);
+      if (c.tf32)
+        tc_mma<true>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
+      else
+        tc_mma<false>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
+    }
+    tc_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    cycles_out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+int main() {
+  int dev = 0, sms = 0, khz = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+  const size_t smem = 4 * (128 * 128 + 256 * 128) + 1024 + 64;
+  if (cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    printf("cudaFuncSetAttribute failed\n");
+    return 1;
+  }
+  long long* d = nullptr;
+  cudaMalloc(&d, sizeof(long long) * sms);
+  long long* h = (long long*)malloc(sizeof(long long) * sms);
+  printf("device %d: %d SMs, nominal %.0f MHz\n", dev, sms, khz / 1000.0);
+  printf("%-5s %4s %4s %5s | %10s | %10s | %s\n", "kind", "M", "N", "nacc", "cyc/MMA", "MAC/cyc/SM", "of the 1x-rate floor max(M,128)*N/256");
+  const int Ms[2] = {128, 64}, Ns[5] = {32, 64, 128, 192, 256}, accs[3] = {1, 2, 4};
+  for (int tf32 = 1; tf32 >= 0; --tf32)
+    for (int mi = 0; mi < 2; ++mi)
+      for (int ni = 0; ni < 5; ++ni)
+        for (int ai = 0; ai < 3; ++ai) {
+          Cfg c{tf32, Ms[mi], Ns[ni], accs[ai], 4096};
+          const int acc_cols = c.N < 32 ? 32 : c.N;
+          if (c.nacc * acc_cols > 512) continue;
+          for (int rep = 0; rep < 2; ++rep) {  // first launch warms up
+            probe_kernel<<<sms, 128, smem>>>(c, d);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) {
+              printf("launch failed (%s) for kind=%s M=%d N=%d nacc=%d\n", cudaGetErrorString(e), tf32 ? "tf32" : "bf16", c.M,
+                     c.N, c.nacc);
+              return 1;
+            }
+          }
+          cudaMemcpy(h, d, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+          long long worst = 0;
+          for (int i = 0; i < sms; ++i) worst = h[i] > worst ? h[i] : worst;
+          const double cyc = (double)worst / c.iters;
+          const int kk = tf32 ? 8 : 16;
+          const double floor_c = (double)(c.M > 128 ? c.M : 128) * c.N / 256.0;
+          printf("%-5s %4d %4d %5d | %10.1f | %10.0f | %.2fx\n", tf32 ? "tf32" : "bf16", c.M, c.N, c.nacc, cyc,
+                 (double)c.M * c.N * kk / cyc, cyc / floor_c);
+        }
+  cudaFree(d);
+  free(h);
+  return 0;
+}
