@@ -95,3 +95,108 @@ def test_metrics_follow_utils(ref):
     want = U.label_accuracy_score(lt, lp, 21)
     hist = sum(O.fast_hist(a.flatten(), b.flatten(), 21) for a, b in zip(lt, lp))
     assert np.allclose(O.hist_to_metrics(hist), want, rtol=1e-12, equal_nan=True)
+
+
+def test_reference_trainer_forward_szn_unmodified(ref, tmp_path, monkeypatch):
+    """The UNMODIFIED ``trainer_fcn.Trainer`` (stub ``pytz``; ``forward_szn`` is the trainer entry point that still runs on
+    torch 2.x — ``forward`` indexes a 0-dim loss, ``trainer_fcn.py:107``) with the shipped 20-d PASCAL table: its table
+    setup (``trainer_fcn.py:44-64``) and its model -> loss -> stitched-labels sequence (``:123-143``) against the oracle
+    and against the product's host-side table split."""
+    import datetime
+    import importlib.util
+    import os
+    import sys
+    import types
+    M, U = ref
+    root = ref_import.reference_root()
+    pytz = types.ModuleType("pytz")
+    pytz.timezone = lambda name: datetime.timezone(datetime.timedelta(hours=-5))
+    monkeypatch.setitem(sys.modules, "pytz", pytz)
+    monkeypatch.setitem(sys.modules, "utils", U)     # the trainer's `import utils` / `import vis_utils` (generic names)
+    monkeypatch.syspath_prepend(root)
+    monkeypatch.chdir(root)                          # embedding pickles are opened by relative path (trainer_fcn.py:49)
+    before = set(sys.modules)
+    try:
+        spec = importlib.util.spec_from_file_location("szn_reference_trainer_fcn", os.path.join(root, "trainer_fcn.py"))
+        T = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(T)
+        D, C, H, W, unseen = 20, 21, 37, 45, [3, 7, 15]
+        params = O.init_params(D, seed=55)
+        model = M.FCN32s(D)
+        model.load_state_dict(params)
+        model.eval()
+        loader = types.SimpleNamespace(dataset=types.SimpleNamespace(class_names=["c%d" % i for i in range(C)]))
+        tr = T.Trainer(cuda=False, model=model, optimizer=None, train_loader=loader, val_loader=loader,
+                       log_dir=str(tmp_path), dataset="pascal", max_epoch=1, tb_writer=None, pixel_embeddings=D,
+                       loss_func="cos", unseen=unseen, val_unseen=[15], label_names=None, forced_unseen=False)
+        table = tr.embeddings.data.clone()
+        assert table.shape == (C, D) and tr.n_class == C and tr.seen == [c for c in range(C) if c not in unseen]
+        # table setup: oracle restatement and the product's host-side helper
+        st, ut = O.split_tables(table, unseen)
+        assert torch.equal(tr.seen_embeddings.data, st) and torch.equal(tr.unseen_embeddings.data, ut)
+        from zeroshotsemanticsegmentation_b200 import utils as PU
+        ps, pu = PU.split_embeddings(table, unseen)
+        assert torch.equal(ps, st) and torch.equal(pu, ut)
+        # the call sequence
+        x, lab, _ = O.synth_batch(1, H, W, C, D, seed=55, block=8)
+        te = O.target_embed_from_labels(lab, table)
+        fcn_score, loss, lbl_pred, lbl_true = tr.forward_szn(x, (lab, te))
+        assert torch.equal(lbl_true, lab)
+        p = {k: v.clone() for k, v in params.items()}
+        with torch.no_grad():
+            f, s = O.forward(x, p, "both")
+        assert rel(f, fcn_score) < 1e-6
+        assert abs(O.cosine_loss(f, lab, te).item() - loss.item()) < 1e-6
+        with torch.no_grad():
+            f_ref, s_ref = model(x, mode="both")
+        assert (O.infer_lbl_szn(f_ref, s_ref, st, ut) == lbl_pred).all()
+        assert (tr.train_log_headers[2], tr.val_log_headers[-1]) == ("train/loss", "elapsed_time") and len(tr.val_log_headers) == 16
+    finally:
+        for k in set(sys.modules) - before:
+            del sys.modules[k]
+
+
+def test_reference_seenmask_trainer_forward_unmodified(ref, tmp_path, monkeypatch):
+    """The UNMODIFIED ``trainer_seenmask.Trainer.forward`` (``trainer_seenmask.py:50-70``): binary target from the label
+    map, ``mode='seenmask'``, mean cross entropy, arg-max of the two channels — against the oracle and the product's
+    device-agnostic ``utils.seenmask_target``."""
+    import datetime
+    import importlib.util
+    import os
+    import sys
+    import types
+    M, U = ref
+    root = ref_import.reference_root()
+    pytz = types.ModuleType("pytz")
+    pytz.timezone = lambda name: datetime.timezone(datetime.timedelta(hours=-5))
+    monkeypatch.setitem(sys.modules, "pytz", pytz)
+    monkeypatch.setitem(sys.modules, "utils", U)
+    monkeypatch.syspath_prepend(root)
+    before = set(sys.modules)
+    try:
+        spec = importlib.util.spec_from_file_location("szn_reference_trainer_seenmask",
+                                                      os.path.join(root, "trainer_seenmask.py"))
+        T = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(T)
+        D, C, H, W, unseen = 5, 21, 30, 41, [0, 12]
+        params = O.init_params(D, seed=56)
+        model = M.FCN32s(D)
+        model.load_state_dict(params)
+        model.eval()
+        loader = types.SimpleNamespace(dataset=types.SimpleNamespace(class_names=["c%d" % i for i in range(C)]))
+        tr = T.Trainer(cuda=False, model=model, optimizer=None, train_loader=loader, val_loader=loader,
+                       log_dir=str(tmp_path), dataset="pascal", max_epoch=1, tb_writer=None, checkpoint={}, unseen=unseen)
+        x, lab, table = O.synth_batch(2, H, W, C, D, seed=56, block=8)
+        score, loss, lbl_pred, lbl_true = tr.forward(x, (lab, O.target_embed_from_labels(lab, table)))
+        tgt = O.seenmask_target(lab, unseen, C)
+        assert torch.equal(lbl_true, tgt)
+        from zeroshotsemanticsegmentation_b200 import utils as PU
+        assert torch.equal(PU.seenmask_target(lab, unseen, C), tgt)   # -1 -> 0 ("unseen"), as upstream
+        with torch.no_grad():
+            s = O.forward(x, {k: v.clone() for k, v in params.items()}, "seenmask")
+        assert rel(s, score) < 1e-6
+        assert abs(O.cross_entropy2d(s, tgt, size_average=True).item() - loss.item()) < 1e-6
+        assert (score.detach().max(1)[1].numpy() == lbl_pred).all()
+    finally:
+        for k in set(sys.modules) - before:
+            del sys.modules[k]
