@@ -168,6 +168,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fused-head", action="store_true",
+                    help="EXPERIMENTAL: FCN32s(fused_head=True), loss / labels / d s17 from the 17x17 score map (not the default, "
+                         "not a bench line until its GPU parity tests are green)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch:
@@ -195,7 +198,7 @@ def main():
     _lib.load()
 
     B, D, C = cfg["B"], cfg["D"], cfg["C"]
-    model = synth.init_model_(szn.FCN32s(D, precision=cfg["precision"]), seed=1337).to(dev).train()
+    model = synth.init_model_(szn.FCN32s(D, precision=cfg["precision"], fused_head=args.fused_head), seed=1337).to(dev).train()
     reducer = ddp.GradientAllReduce(model)
     # every rank draws its own images (seed + rank), like a sharded loader would
     x_h, lab_h, table = synth.synth_batch(B, H, W, C, D, seed=1337 + rank)
@@ -208,7 +211,7 @@ def main():
         f = model(x, mode="fcn")
         loss = U.cosine_loss(f, lab, table=table, accum_hook=reducer.accum_hook)
         loss.backward()
-        lbl = U.infer_lbl_device(f.detach(), table)
+        lbl = U.infer_lbl_device(f if args.fused_head else f.detach(), table)  # detach() would drop the fused-head handle
         return loss, lbl
 
     def barrier():
@@ -377,7 +380,8 @@ def main():
         "config": {"workload": cfg["name"], "batch_per_gpu": B, "global_batch": B * world, "H": H, "W": W, "D": D, "C": C,
                    "loss": "cosine", "mode": "train (Dropout2d live)", "parallelism": "dp%d" % world,
                    "l2": "no explicit flush: one step streams >10 GB of activations per GPU, far above the 126 MB L2",
-                   "weights": "seeded random init (no network for VGG16 weights)"},
+                   "weights": "seeded random init (no network for VGG16 weights)",
+                   **({"fused_head": "EXPERIMENTAL"} if args.fused_head else {})},
         "gpu_launches": launches,
         "step_tflops": (fwd + bwd) * B * world / (ms_step / 1e3) / 1e12,
         "roofline": {"bound": "tensor", "kernel": "umma_conv_kernel<T,MODE> (tcgen05 implicit-GEMM conv fwd/dgrad/wgrad)",

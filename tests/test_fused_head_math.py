@@ -34,3 +34,21 @@ def test_fused_head_equals_materialised_path(B, D, C, H, W, hs, ws):
     assert abs(loss.item() - loss_ref.item()) < 1e-10
     assert torch.allclose(ds17, g_ref, rtol=1e-8, atol=1e-12)
     assert (labels.numpy() == lbl_ref).all()
+
+
+@pytest.mark.parametrize("B,D,C,H,W,hs,ws", [(2, 6, 7, 40, 56, 2, 3), (1, 5, 9, 70, 33, 3, 2), (1, 4, 3, 5, 3, 1, 1)])
+def test_kernel_emulation_equals_the_algebra(B, D, C, H, W, hs, ws):
+    """tools/fused_head_emulate.py follows csrc/szn_fused_head.cu index for index (cells, taps, Gram pairs, M2 expansion,
+    gather around a node); it must reproduce the dense-matrix algebra above."""
+    import fused_head_emulate as EM
+    g = torch.Generator().manual_seed(H + 1)
+    s17 = torch.randn(B, D, hs, ws, generator=g, dtype=torch.float64)
+    _, lab, table = O.synth_batch(B, H, W, C, D, seed=H + 1, block=4, ignore_frac=0.1)
+    table = table.double()
+    table[C // 2] = 0  # a zero row: similarity exactly 0, never a target here
+    lab[lab == C // 2] = -1
+    loss_a, labels_a, ds_a = FH.fused_cosine_head(s17, lab, table)
+    loss_e, labels_e, ds_e = EM.fused_cosine_head(s17.numpy(), lab.numpy(), table.numpy())
+    assert abs(loss_e - loss_a.item()) < 1e-12
+    assert (labels_e == labels_a.numpy()).all()
+    assert abs(ds_e - ds_a.numpy()).max() < 1e-12 * max(1.0, abs(ds_a.numpy()).max())

@@ -91,6 +91,22 @@ def is_diag_bilinear(w):
     return int(torch.count_nonzero(w)) == int(torch.count_nonzero(diag))
 
 
+class ScoreHandle:
+    """Attached to a score returned by ``FCN32s(fused_head=True)``: the hs x ws map ``s17`` ([B,hs,ws,Dp] fp32, an autograd
+    output of the same node) the score was upsampled from.  ``valid_for`` is false once the score has been modified in
+    place or is another tensor (``detach()``, slicing, arithmetic make new tensors without the handle)."""
+
+    def __init__(self, s17, score):
+        self.s17 = s17
+        self.D = score.shape[1]
+        self.hw = (score.shape[2], score.shape[3])
+        self._version = score._version
+        self._ptr = score.data_ptr()
+
+    def valid_for(self, score):
+        return score._version == self._version and score.data_ptr() == self._ptr and tuple(score.shape[2:]) == self.hw
+
+
 def _finish(module, grads):
     if module._grad_flush is not None:
         module._grad_flush()
@@ -207,10 +223,16 @@ class FCN32sFunction(torch.autograd.Function):
         ctx.module = module
         ctx.saved = dict(x=x, acts=acts, dims=dims, h6=h6, h7=h7, s17=s17, drop=drop, P=P, head_w=head_w,
                          geom=(B, H, W, D, Dp, hs, ws), diag=diag, dt=dt, tdtype=tdtype)
+        if getattr(module, "fused_head", False) and diag:
+            # experimental: also hand out the hs x ws score map, so that the fused head (utils._FusedHeadLoss) can send its
+            # gradient straight back as d s17 without the (B, D, H, W) tensor ever being read
+            # (a fresh view: the tensor kept in ctx.saved must not become an autograd output, or ctx -> s17 -> grad_fn ->
+            # ctx would keep every activation of the step alive until the cycle collector runs)
+            return f, s, s17.view(s17.shape)
         return f, s
 
     @staticmethod
-    def backward(ctx, gf, gs):
+    def backward(ctx, gf, gs, gs17=None):
         sv = ctx.saved
         module = ctx.module
         dt, tdtype = sv["dt"], sv["tdtype"]
@@ -233,9 +255,13 @@ class FCN32sFunction(torch.autograd.Function):
             return torch.zeros(shape, device=dev, dtype=dtype)
 
         # ---------------- heads: d s17 ----------------
-        if gf is None and gs is None:
+        if gf is None and gs is None and gs17 is None:
             return _finish(module, grads)
         ds17 = zeros((B, hs, ws, Dp), tdtype)
+        if gs17 is not None and gf is None:
+            # fused head: d s17 arrives ready-made (fp32); store it in the trunk's gradient type (TF32-rounded / bf16).
+            # Runs before the seen-mask head below, which overwrites its own two channels.
+            call("szn_cast", dt, ptr(gs17.contiguous().float()), ptr(ds17), ds17.numel(), st)
         if gf is not None:
             gf = gf.contiguous()
             if sv["diag"]:
@@ -247,6 +273,10 @@ class FCN32sFunction(torch.autograd.Function):
                 g = torch.empty_like(P["upscore.weight"])
                 call("szn_deconv_small_wgrad", ptr(sv["s17"]), ptr(gf), ptr(g), B, D, D, H, W, hs, ws, Dp, 0, st)
                 grads["upscore.weight"] = g
+        if gs17 is not None and gf is not None:
+            # the score was used both through the fused head and as a tensor: add the two contributions (rare)
+            both = ds17.float() + gs17.float()
+            call("szn_cast", dt, ptr(both), ptr(ds17), ds17.numel(), st)
         if gs is not None:
             gs = gs.contiguous()
             call("szn_deconv_small_dgrad", dt, ptr(gs), ptr(P["seenmask_upscore.weight"].detach().contiguous()),
@@ -264,7 +294,7 @@ class FCN32sFunction(torch.autograd.Function):
         rows17 = B * hs * ws
         # a head whose output received no gradient (mode='fcn' / 'seenmask') gets None, as autograd gives the reference,
         # not zeros: an optimizer with momentum / weight decay would otherwise move parameters that were not used
-        want = {"score_fr": gf is not None, "seenmask_score": gs is not None}
+        want = {"score_fr": gf is not None or gs17 is not None, "seenmask_score": gs is not None}
         if any(need[k + ".weight"] and want[k] for k in want):
             dwh = zeros((Dp, 4096))
             call("szn_conv_wgrad", dt, ptr(sv["h7"]), ptr(ds17), ptr(dwh), B, hs, ws, 4096, Dp, 1, 1, 0, Dp, st)

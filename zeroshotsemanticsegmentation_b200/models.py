@@ -43,14 +43,20 @@ class FCN32s(nn.Module):
                  or ``"bf16"`` (bf16 storage and products, fp32 accumulate).
       upscore_weight_grad: also compute the dense ``upscore.weight.grad`` (213 GFLOP/image at D=300 for a
                  weight the reference never optimises, ``train.py:324-327``); off by default.
+      fused_head: EXPERIMENTAL, off by default, not yet validated on a GPU.  The returned score carries a handle to the
+                 17x17 score map it was upsampled from; ``utils.cosine_loss(score, target, table=E)`` and
+                 ``utils.infer_lbl*`` then work from that map (``szn_head_fused_*``) instead of making four passes over
+                 the (B, D, H, W) tensor, and the loss gradient re-enters the network as d s17.  Any other use of the
+                 score (or an in-place change of it) silently takes the ordinary path.
     """
 
-    def __init__(self, n_class=21, precision="tf32", upscore_weight_grad=False):
+    def __init__(self, n_class=21, precision="tf32", upscore_weight_grad=False, fused_head=False):
         super().__init__()
         if precision not in engine.PRECISIONS:
             raise ValueError("precision must be one of %s" % list(engine.PRECISIONS))
         self.precision = precision
         self.upscore_weight_grad = upscore_weight_grad
+        self.fused_head = bool(fused_head)
         for row in engine.TRUNK:
             if len(row) == 1:
                 setattr(self, row[0], nn.MaxPool2d(2, stride=2, ceil_mode=True))
@@ -100,7 +106,10 @@ class FCN32s(nn.Module):
             raise Exception("model given unexpected forward mode")
         if not x.is_cuda:
             raise RuntimeError("FCN32s (B200 build) runs on CUDA only: move the model and input to the GPU")
-        f, s = engine.FCN32sFunction.apply(self, x, *self._ordered_params())
+        out = engine.FCN32sFunction.apply(self, x, *self._ordered_params())
+        f, s = out[0], out[1]
+        if len(out) == 3:  # fused_head: the score remembers the map it came from (see utils.ScoreHandle)
+            f._szn_head = engine.ScoreHandle(out[2], f)
         if mode == "fcn":
             return f
         if mode == "seenmask":

@@ -99,6 +99,56 @@ class _EmbedLoss(torch.autograd.Function):
         return g, None, None, None, None, None
 
 
+def _fused_handle(score):
+    """The ScoreHandle of a score returned by ``FCN32s(fused_head=True)`` if it still describes ``score``, else None."""
+    head = getattr(score, "_szn_head", None)
+    return head if head is not None and head.valid_for(score) else None
+
+
+def _fused_workspace(s17, C):
+    B, hs, ws, _ = s17.shape
+    n = int(_lib.load().szn_head_fused_workspace_floats(B, hs, ws, C))
+    return torch.empty(n, device=s17.device, dtype=torch.float32)
+
+
+class _FusedHeadLoss(torch.autograd.Function):
+    """EXPERIMENTAL: ``cosine_loss`` on the hs x ws score map (``szn_head_fused_*``); input and gradient are
+    [B,hs,ws,Dp] fp32, the (B, D, H, W) score tensor is not touched."""
+
+    @staticmethod
+    def forward(ctx, s17, target, table, D, hw, accum_hook):
+        _check_cuda(s17, target, table)
+        B, hs, ws, ld = s17.shape
+        H, W = hw
+        sc = s17.detach().contiguous().float()
+        tg = target.detach().contiguous().long()
+        tb = _as_f32(table)
+        if tb.shape[1] != D or tuple(tg.shape) != (B, H, W):
+            raise ValueError("fused head: table / target do not match the score")
+        C = tb.shape[0]
+        work = _fused_workspace(sc, C)
+        accum = torch.empty(2, device=sc.device, dtype=torch.float64)
+        loss = torch.empty((), device=sc.device, dtype=torch.float32)
+        st = _lib.stream()
+        call("szn_head_fused_fwd", ptr(sc), ld, 0, ptr(tg), ptr(tb), B, D, H, W, hs, ws, C, ptr(work), ptr(accum), ptr(loss),
+             None, st)
+        if accum_hook is not None:
+            accum_hook(accum)
+            call("szn_loss_finalize", 0, ptr(accum), ptr(loss), st)
+        ctx.saved = (sc, tb, work, accum, D)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        sc, tb, work, accum, D = ctx.saved
+        B, hs, ws, ld = sc.shape
+        ds = torch.empty_like(sc)
+        go = gout.detach().contiguous().float()
+        call("szn_head_fused_bwd", ptr(sc), ld, 0, ptr(tb), B, D, hs, ws, tb.shape[0], ptr(work), ptr(accum), ptr(go), ptr(ds),
+             _lib.stream())
+        return ds, None, None, None, None, None
+
+
 class _CrossEntropy2d(torch.autograd.Function):
     @staticmethod
     def forward(ctx, score, target, size_average, accum_hook):
@@ -143,12 +193,26 @@ def mse_loss(score, target, target_embed=None, table=None, accum_hook=None):
 
 def cosine_loss(score, target, target_embed=None, table=None, accum_hook=None):
     """(N - sum_valid cos(score_p, target_embed_p)) / N (``utils.py:75-102``)."""
+    head = _fused_handle(score) if target_embed is None and table is not None else None
+    if head is not None:  # experimental FCN32s(fused_head=True): work from the 17x17 map the score was upsampled from
+        return _FusedHeadLoss.apply(head.s17, target, table, head.D, head.hw, accum_hook)
     return _EmbedLoss.apply(score, target, target_embed, table, 0, accum_hook)
 
 
 def _labels_device(score, embed_arr):
     _check_cuda(score, embed_arr)
     n, c, h, w = score.shape
+    head = _fused_handle(score)
+    if head is not None:  # experimental FCN32s(fused_head=True)
+        s17 = head.s17.detach().contiguous().float()
+        tb = _as_f32(embed_arr)
+        if tb.shape[1] != c:
+            raise ValueError("embedding width %d does not match score channels %d" % (tb.shape[1], c))
+        out = torch.empty((n, h, w), device=score.device, dtype=torch.int64)
+        work = _fused_workspace(s17, tb.shape[0])
+        call("szn_head_fused_fwd", ptr(s17), s17.shape[3], 0, None, ptr(tb), n, c, h, w, s17.shape[1], s17.shape[2],
+             tb.shape[0], ptr(work), None, None, ptr(out), _lib.stream())
+        return out
     sc, tb = _as_f32(score), _as_f32(embed_arr)
     C, D = tb.shape
     if D != c:
