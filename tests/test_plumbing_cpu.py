@@ -1,0 +1,141 @@
+"""The Python glue of the GPU path, exercised on the CPU with the kernels stubbed out: every C-ABI call made by
+``engine.FCN32sFunction`` (forward and backward), the losses, the label functions and the experimental fused head is
+checked against the ctypes signature it is bound with (argument count, integer vs pointer), and autograd checks every
+returned gradient against its parameter's shape.  Values are garbage (no kernel runs): this pins control flow, shapes and
+call order only — numerics are the GPU tests' job."""
+import ctypes
+
+import pytest
+import torch
+
+from zeroshotsemanticsegmentation_b200 import _lib, engine, models, utils
+
+
+class Recorder:
+    def __init__(self):
+        self.names = []
+
+    def __call__(self, name, *args):
+        sig = _lib.SIGNATURES[name]
+        assert len(args) == len(sig), "%s: %d arguments for %d parameters" % (name, len(args), len(sig))
+        for i, (a, t) in enumerate(zip(args, sig)):
+            if t is ctypes.c_void_p:
+                assert a is None or isinstance(a, int), "%s arg %d: pointer expected, got %r" % (name, i, type(a))
+            elif t is ctypes.c_float:
+                assert isinstance(a, float), "%s arg %d: float expected, got %r" % (name, i, type(a))
+            else:
+                assert isinstance(a, int) and not isinstance(a, bool), "%s arg %d: int expected, got %r" % (name, i, type(a))
+        self.names.append(name)
+
+
+@pytest.fixture()
+def stubbed(monkeypatch):
+    rec = Recorder()
+    for mod in (_lib, engine, utils):
+        monkeypatch.setattr(mod, "call", rec, raising=True)
+    monkeypatch.setattr(_lib, "stream", lambda: 0)
+    monkeypatch.setattr(utils, "_check_cuda", lambda *ts: None)
+    return rec
+
+
+def run(model, x, mode="fcn"):
+    out = engine.FCN32sFunction.apply(model, x, *model._ordered_params())
+    if len(out) == 3:
+        out[0]._szn_head = engine.ScoreHandle(out[2], out[0])
+    return out[0], out[1]
+
+
+D, C, H, W = 5, 7, 8, 12
+
+
+def inputs(B=1):
+    g = torch.Generator().manual_seed(0)
+    return (torch.randn(B, 3, H, W, generator=g), torch.randint(-1, C, (B, H, W), generator=g),
+            torch.randn(C, D, generator=g))
+
+
+def test_default_path_calls_and_gradient_shapes(stubbed):
+    m = models.FCN32s(D).train()
+    x, lab, table = inputs(2)
+    f, s = run(m, x)
+    assert f.shape == (2, D, H, W) and s.shape == (2, 2, H, W) and f.is_contiguous()
+    fwd = list(stubbed.names)
+    assert fwd[0] == "szn_conv1_1_fwd" and fwd.count("szn_conv_fwd") == 15 and fwd.count("szn_pool_fwd") == 5
+    assert fwd[-2:] == ["szn_upsample32_crop_fwd", "szn_deconv_small_fwd"] and "szn_dropout_scale" in fwd
+    loss = utils.cosine_loss(f, lab, table=table)
+    del stubbed.names[:]
+    loss.backward()   # autograd validates every gradient's shape against its parameter
+    bwd = stubbed.names
+    assert bwd[0] == "szn_embed_loss_bwd" and "szn_upsample32_crop_bwd" in bwd
+    assert bwd.count("szn_conv_wgrad") == 15 and bwd.count("szn_conv_dgrad") == 15 and bwd.count("szn_pool_bwd") == 5
+    assert bwd[-1] == "szn_conv1_1_wgrad"
+    for n, p in m.named_parameters():
+        if "upscore" in n or n.startswith("seenmask"):
+            assert p.grad is None, n                     # unused head / frozen filter: None, not zeros
+        else:
+            assert p.grad is not None and p.grad.shape == p.shape, n
+    assert m.conv3_2.weight.grad.stride() == m.conv3_2.weight.stride()   # the wgrad buffer is adopted without a copy
+    labels = utils.infer_lbl_device(f.detach(), table)
+    assert labels.shape == (2, H, W) and labels.dtype == torch.int64
+
+
+def test_both_heads_and_frozen_trunk(stubbed):
+    m = models.FCN32s(D).eval()
+    x, lab, table = inputs()
+    for p in m.parameters():
+        p.requires_grad = False
+    for p in list(m.seenmask_score.parameters()) + list(m.seenmask_upscore.parameters()):
+        p.requires_grad = True
+    f, s = run(m, x)
+    assert "szn_dropout_scale" not in stubbed.names      # eval mode: no masks
+    loss = utils.cross_entropy2d(s, (lab >= 0).long(), size_average=True, accum_hook=lambda acc: None)
+    assert stubbed.names[-1] == "szn_loss_finalize"      # the hook re-finalises the loss from the (all-reduced) accumulator
+    del stubbed.names[:]
+    loss.backward()
+    assert "szn_conv_dgrad" not in stubbed.names and stubbed.names.count("szn_conv_wgrad") == 1   # head GEMM only
+    assert m.seenmask_score.weight.grad.shape == (2, 4096, 1, 1) and m.seenmask_upscore.weight.grad.shape == (2, 2, 64, 64)
+    assert m.score_fr.weight.grad is None and m.conv1_1.weight.grad is None
+    out = utils._stitch(f.detach(), table, table, seen_mask_score=s.detach())
+    assert out.shape == (1, H, W)
+
+
+def test_experimental_fused_head_routes_through_the_score_map(stubbed):
+    m = models.FCN32s(D, fused_head=True).eval()
+    x, lab, table = inputs(2)
+    f, s = run(m, x)
+    head = utils._fused_handle(f)
+    assert head is not None and head.s17.shape == (2, 1, 1, 64) and head.D == D and head.hw == (H, W)
+    assert utils._fused_handle(f.detach()) is None       # another tensor object: ordinary path
+    del stubbed.names[:]
+    loss = utils.cosine_loss(f, lab, table=table)
+    assert stubbed.names == ["szn_head_fused_fwd"]
+    labels = utils.infer_lbl_device(f, table)
+    assert stubbed.names[-1] == "szn_head_fused_fwd" and labels.shape == (2, H, W)
+    del stubbed.names[:]
+    loss.backward()
+    assert stubbed.names[0] == "szn_head_fused_bwd" and stubbed.names[1] == "szn_cast"
+    assert "szn_upsample32_crop_bwd" not in stubbed.names and "szn_embed_loss_bwd" not in stubbed.names
+    assert m.score_fr.weight.grad.shape == m.score_fr.weight.shape and m.conv1_1.weight.grad is not None
+    assert m.seenmask_score.weight.grad is None
+    # an explicit target_embed, or a score that was modified, takes the ordinary path
+    f2, _ = run(m, x)
+    del stubbed.names[:]
+    utils.cosine_loss(f2, lab, torch.zeros(2, D, H, W))
+    assert stubbed.names == ["szn_embed_loss_fwd"]
+    f3, _ = run(m, x)
+    with torch.no_grad():
+        f3.mul_(2.0)
+    assert utils._fused_handle(f3) is None
+
+
+def test_optimizers_call_their_kernels_with_bound_signatures(stubbed, monkeypatch):
+    from zeroshotsemanticsegmentation_b200 import optim
+    monkeypatch.setattr(optim, "call", stubbed)
+    p = torch.nn.Parameter(torch.zeros(4, 3, 3, 3).contiguous(memory_format=torch.channels_last))
+    p.grad = torch.zeros(4, 3, 3, 3)                      # NCHW gradient for a channels_last parameter: re-laid out
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))  # let the CPU tensors pass the device check
+    for opt in (optim.FusedSGD([p], lr=0.1, momentum=0.9), optim.FusedAdam([p], lr=1e-3)):
+        v0 = p._version
+        opt.step()
+        assert p._version == v0 + 1                       # the packed-weight cache sees the update
+    assert stubbed.names[-2:] == ["szn_sgd_step", "szn_adam_step"]
