@@ -130,18 +130,18 @@ int szn_stitch_labels(const long long* lbl_seen, const long long* lbl_unseen, co
                       const long long* target, const long long* unseen, int n_unseen, int n, int h, int w,
                       long long* out, void* stream);
 
-/* ---- EXPERIMENTAL, opt-in (FCN32s(fused_head=True)), not on the default path: cosine loss (utils.py:75-102), labels
- * (utils.py:159-185) and the gradient of the hs x ws score map computed from that map alone; the (B, D, H, W) score
+/* ---- EXPERIMENTAL, opt-in (FCN32s(fused_head=True)), not on the default path: cosine loss (kind 0, utils.py:75-102) or
+ * MSE loss (kind 1, utils.py:50-73), labels (utils.py:159-185) and the gradient of the hs x ws score map computed from that map alone; the (B, D, H, W) score
  * tensor (models.py:94,146-147) is neither read nor written.  s17: fp32 [B,hs,ws,ld], channels [coff, coff+D);
  * target: int64 [B,H,W] (-1 = ignore) or null (labels only); labels: int64 [B,H,W] or null; accum = {sum cos, n_valid}.
  * workspace: szn_head_fused_workspace_floats(B, hs, ws, C) floats, shared by fwd and bwd of one step.
  * bwd writes ds17 fp32 [B,hs,ws,ld]: grad_out/N * dL/ds in channels [coff, coff+D), 0 elsewhere; N = accum[1], which the
- * caller may all-reduce between the two calls (then szn_loss_finalize(0, ...) gives the global loss). */
+ * caller may all-reduce between the two calls (then szn_loss_finalize(kind, ...) gives the global loss). */
 long long szn_head_fused_workspace_floats(int B, int hs, int ws, int C);
-int szn_head_fused_fwd(const float* s17, int ld, int coff, const long long* target, const float* table, int B, int D, int H,
-                       int W, int hs, int ws, int C, float* workspace, double* accum, float* loss, long long* labels,
-                       void* stream);
-int szn_head_fused_bwd(const float* s17, int ld, int coff, const float* table, int B, int D, int hs, int ws, int C,
+int szn_head_fused_fwd(int kind, const float* s17, int ld, int coff, const long long* target, const float* table, int B,
+                       int D, int H, int W, int hs, int ws, int C, float* workspace, double* accum, float* loss,
+                       long long* labels, void* stream);
+int szn_head_fused_bwd(int kind, const float* s17, int ld, int coff, const float* table, int B, int D, int hs, int ws, int C,
                        const float* workspace, const double* accum, const float* grad_out, float* ds17, void* stream);
 
 /* ---- optimizer step (train.py:126-129 SGD param groups; trainer_fcn.py:158 optim.step()) ----

@@ -52,10 +52,21 @@ def test_fused_kernels_equal_materialised_head(B, D, C, H, W):
     assert float(ds[..., D:].abs().max()) == 0.0
     work = U._fused_workspace(s17, C)
     lbl = torch.empty(B, H, W, dtype=torch.int64, device=DEV)
-    _lib.call("szn_head_fused_fwd", s17.data_ptr(), Dp, 0, None, table.data_ptr(), B, D, H, W, hs, ws, C, work.data_ptr(),
+    _lib.call("szn_head_fused_fwd", 0, s17.data_ptr(), Dp, 0, None, table.data_ptr(), B, D, H, W, hs, ws, C, work.data_ptr(),
               None, None, lbl.data_ptr(), st())
     torch.cuda.synchronize()
     assert float((lbl != lbl_ref).float().mean()) < 1e-3  # another summation order: near-ties only
+    # the MSE variant (utils.py:50-73) from the same quantities
+    f2 = f.detach().clone().requires_grad_(True)
+    mse_ref = U.mse_loss(f2, lab, table=table)
+    (gf2,) = torch.autograd.grad(mse_ref, f2)
+    ds_ref2 = torch.zeros(B, hs, ws, Dp, device=DEV)
+    _lib.call("szn_upsample32_crop_bwd", 0, gf2.data_ptr(), ds_ref2.data_ptr(), B, D, H, W, hs, ws, Dp, 0, st())
+    s2 = s17.clone().requires_grad_(True)
+    mse = U._FusedHeadLoss.apply(s2, lab, table, D, (H, W), None, 1)
+    (ds2,) = torch.autograd.grad(mse, s2)
+    assert abs(mse.item() - mse_ref.item()) < 1e-4 * max(1.0, abs(mse_ref.item()))
+    assert float((ds2[..., :D] - ds_ref2[..., :D]).norm() / ds_ref2[..., :D].norm()) < 1e-3
 
 
 def test_model_with_fused_head_equals_default_path():

@@ -13,8 +13,9 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import fused_head_math as FH  # noqa: E402
 
 
+@pytest.mark.parametrize("kind", [0, 1], ids=["cos", "mse"])
 @pytest.mark.parametrize("B,D,C,H,W,hs,ws", [(2, 6, 7, 40, 56, 2, 3), (1, 5, 9, 70, 33, 3, 2), (1, 4, 3, 5, 3, 1, 1)])
-def test_fused_head_equals_materialised_path(B, D, C, H, W, hs, ws):
+def test_fused_head_equals_materialised_path(B, D, C, H, W, hs, ws, kind):
     g = torch.Generator().manual_seed(H)
     s17 = torch.randn(B, D, hs, ws, generator=g, dtype=torch.float64, requires_grad=True)
     _, lab, table = O.synth_batch(B, H, W, C, D, seed=H, block=4, ignore_frac=0.1)
@@ -27,17 +28,19 @@ def test_fused_head_equals_materialised_path(B, D, C, H, W, hs, ws):
     P = FH.tap_matrix(H, W, hs, ws)
     up2 = torch.einsum("pk,bdk->bdp", P, s17.detach().reshape(B, D, hs * ws)).reshape(B, D, H, W)
     assert torch.allclose(up2, up.detach(), atol=1e-12)
-    loss_ref = O.cosine_loss(up, lab, O.target_embed_from_labels(lab, table))
+    loss_fn = O.cosine_loss if kind == 0 else O.mse_loss
+    loss_ref = loss_fn(up, lab, O.target_embed_from_labels(lab, table))
     (g_ref,) = torch.autograd.grad(loss_ref, s17)
     lbl_ref = O.infer_lbl(up.detach(), table)
-    loss, labels, ds17 = FH.fused_cosine_head(s17.detach(), lab, table)
-    assert abs(loss.item() - loss_ref.item()) < 1e-10
+    loss, labels, ds17 = FH.fused_cosine_head(s17.detach(), lab, table, kind)
+    assert abs(loss.item() - loss_ref.item()) < 1e-10 * max(1.0, abs(loss_ref.item()))
     assert torch.allclose(ds17, g_ref, rtol=1e-8, atol=1e-12)
     assert (labels.numpy() == lbl_ref).all()
 
 
+@pytest.mark.parametrize("kind", [0, 1], ids=["cos", "mse"])
 @pytest.mark.parametrize("B,D,C,H,W,hs,ws", [(2, 6, 7, 40, 56, 2, 3), (1, 5, 9, 70, 33, 3, 2), (1, 4, 3, 5, 3, 1, 1)])
-def test_kernel_emulation_equals_the_algebra(B, D, C, H, W, hs, ws):
+def test_kernel_emulation_equals_the_algebra(B, D, C, H, W, hs, ws, kind):
     """tools/fused_head_emulate.py follows csrc/szn_fused_head.cu index for index (cells, taps, Gram pairs, M2 expansion,
     gather around a node); it must reproduce the dense-matrix algebra above."""
     import fused_head_emulate as EM
@@ -47,8 +50,8 @@ def test_kernel_emulation_equals_the_algebra(B, D, C, H, W, hs, ws):
     table = table.double()
     table[C // 2] = 0  # a zero row: similarity exactly 0, never a target here
     lab[lab == C // 2] = -1
-    loss_a, labels_a, ds_a = FH.fused_cosine_head(s17, lab, table)
-    loss_e, labels_e, ds_e = EM.fused_cosine_head(s17.numpy(), lab.numpy(), table.numpy())
-    assert abs(loss_e - loss_a.item()) < 1e-12
+    loss_a, labels_a, ds_a = FH.fused_cosine_head(s17, lab, table, kind)
+    loss_e, labels_e, ds_e = EM.fused_cosine_head(s17.numpy(), lab.numpy(), table.numpy(), kind)
+    assert abs(loss_e - loss_a.item()) < 1e-12 * max(1.0, abs(loss_a.item()))
     assert (labels_e == labels_a.numpy()).all()
     assert abs(ds_e - ds_a.numpy()).max() < 1e-12 * max(1.0, abs(ds_a.numpy()).max())

@@ -111,6 +111,8 @@ def test_experimental_fused_head_routes_through_the_score_map(stubbed):
     assert stubbed.names == ["szn_head_fused_fwd"]
     labels = utils.infer_lbl_device(f, table)
     assert stubbed.names[-1] == "szn_head_fused_fwd" and labels.shape == (2, H, W)
+    utils.mse_loss(f, lab, table=table)
+    assert stubbed.names == ["szn_head_fused_fwd"] * 3
     del stubbed.names[:]
     loss.backward()
     assert stubbed.names[0] == "szn_head_fused_bwd" and stubbed.names[1] == "szn_cast"

@@ -22,7 +22,7 @@ def nodes(s17, table):
     return A, G
 
 
-def pixels(A, G, en_inv, target, H, W, hs, ws):
+def pixels(A, G, en_inv, en2, kind, target, H, W, hs, ws):
     """Per cell (anchor (ia, ja), grid (hs+1) x (ws+1)): labels, sum of cos, count, M1cell (4,C), M2cell (4,4)."""
     B, K, C = A.shape
     cells = (hs + 1) * (ws + 1)
@@ -63,11 +63,15 @@ def pixels(A, G, en_inv, target, H, W, hs, ws):
                         if 0 <= t < C:
                             un2 = sum(w[a] * w[a] * Gc[a] for a in range(4)) + 2 * sum(
                                 w[a] * w[a2] * Gc[e] for (a, a2), e in pair_of.items())
-                            inv_un = 1.0 / np.sqrt(un2)
-                            cs = pa[t] * inv_un * en_inv[t]
-                            tot += cs
+                            if kind == 0:
+                                inv_un = 1.0 / np.sqrt(un2)
+                                cs = pa[t] * inv_un * en_inv[t]
+                                tot += cs
+                                ap, bp = -inv_un, cs * inv_un * inv_un
+                            else:
+                                tot += un2 - 2.0 * pa[t] + en2[t]
+                                ap, bp = -2.0, 2.0
                             cnt += 1
-                            ap, bp = -inv_un, cs * inv_un * inv_un
                             M1[b, cell, :, t] += w * ap
                             for a in range(4):
                                 m2[a] += w[a] * w[a] * bp
@@ -80,7 +84,7 @@ def pixels(A, G, en_inv, target, H, W, hs, ws):
     return labels, tot, cnt, M1, M2
 
 
-def grad(s17, table, en_inv, M1, M2, n_valid, gout=1.0):
+def grad(s17, table, en_inv, kind, M1, M2, n_valid, gout=1.0):
     B, hs, ws, D = s17.shape
     ds = np.zeros_like(s17)
     for b in range(B):
@@ -96,12 +100,12 @@ def grad(s17, table, en_inv, M1, M2, n_valid, gout=1.0):
                     ni, nj = ia + (a2 >> 1), ja + (a2 & 1)
                     if 0 <= ni < hs and 0 <= nj < ws:
                         acc += M2[b, cell, a, a2] * s17[b, ni, nj]
-            acc += (m1n * en_inv) @ table
+            acc += (m1n * en_inv if kind == 0 else m1n) @ table
             ds[b, i, j] = acc * (gout / n_valid)
     return ds
 
 
-def fused_cosine_head(s17_nchw, target, table):
+def fused_cosine_head(s17_nchw, target, table, kind=0):
     """Same interface as tools/fused_head_math.fused_cosine_head (numpy in / out)."""
     s17 = np.ascontiguousarray(np.transpose(s17_nchw, (0, 2, 3, 1))).astype(np.float64)
     table = table.astype(np.float64)
@@ -110,7 +114,7 @@ def fused_cosine_head(s17_nchw, target, table):
     en = np.sqrt((table * table).sum(1))
     en_inv = np.where(en == 0, 1.0, 1.0 / np.where(en == 0, 1.0, en))
     A, G = nodes(s17, table)
-    labels, tot, cnt, M1, M2 = pixels(A, G, en_inv, target, H, W, hs, ws)
-    loss = (cnt - tot) / cnt
-    ds = grad(s17, table, en_inv, M1, M2, cnt)
+    labels, tot, cnt, M1, M2 = pixels(A, G, en_inv, en * en, kind, target, H, W, hs, ws)
+    loss = (cnt - tot) / cnt if kind == 0 else tot / cnt
+    ds = grad(s17, table, en_inv, kind, M1, M2, cnt)
     return loss, labels, np.transpose(ds, (0, 3, 1, 2))

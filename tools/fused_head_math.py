@@ -33,8 +33,9 @@ def tap_matrix(H, W, hs, ws, dtype=torch.float64):
     return torch.einsum("yi,xj->yxij", py, px).reshape(H * W, hs * ws)
 
 
-def fused_cosine_head(s17, target, table):
-    """s17 (B, D, hs, ws), target (B, H, W) int64 with -1 = ignore, table (C, D).
+def fused_cosine_head(s17, target, table, kind=0):
+    """s17 (B, D, hs, ws), target (B, H, W) int64 with -1 = ignore, table (C, D).  kind 0 = cosine_loss, 1 = mse_loss
+    (|u_p - e_t|^2 = |u_p|^2 - 2 u_p.e_t + |e_t|^2; a_p = -2/N on the raw rows, b_p = 2/N).
     Returns (loss, labels (B,H,W), d loss / d s17) computed from hs*ws-sized quantities and per-pixel scalars only."""
     B, D, hs, ws = s17.shape
     _, H, W = target.shape
@@ -60,18 +61,23 @@ def fused_cosine_head(s17, target, table):
         t = target[b].reshape(-1)
         valid = t >= 0
         tc = t.clamp(min=0)
-        cos = PA[torch.arange(H * W), tc] / (un * en[tc])
+        pat = PA[torch.arange(H * W), tc]
+        cos = pat / (un * en[tc]) if kind == 0 else un2 - 2.0 * pat + (en[tc] ** 2)
         total = total + cos[valid].sum()
         stats.append((P, S, un, cos, valid, tc))
-    loss = (n_valid - total) / n_valid
+    loss = (n_valid - total) / n_valid if kind == 0 else total / n_valid
     C = table.shape[0]
     for b, (P, S, un, cos, valid, tc) in enumerate(stats):
-        a = torch.where(valid, -1.0 / (n_valid * un), torch.zeros_like(un))
-        bb = torch.where(valid, cos / (n_valid * un * un), torch.zeros_like(un))
+        if kind == 0:
+            a = torch.where(valid, -1.0 / (n_valid * un), torch.zeros_like(un))
+            bb = torch.where(valid, cos / (n_valid * un * un), torch.zeros_like(un))
+        else:
+            a = torch.where(valid, torch.full_like(un, -2.0 / n_valid), torch.zeros_like(un))
+            bb = torch.where(valid, torch.full_like(un, 2.0 / n_valid), torch.zeros_like(un))
         onehot = torch.zeros(P.shape[0], C, dtype=dt)
         onehot[torch.arange(P.shape[0]), tc] = 1.0
         M1 = P.t() @ (onehot * a[:, None])                  # (hs*ws, C)
         M2 = P.t() @ (P * bb[:, None])                      # (hs*ws, hs*ws), neighbour-sparse
-        grads[b] = M1 @ E_hat + M2 @ S
+        grads[b] = M1 @ (E_hat if kind == 0 else E) + M2 @ S
     ds17 = grads.transpose(1, 2).reshape(B, D, hs, ws)
     return loss, labels, ds17

@@ -41,8 +41,8 @@ SIGNATURES = {
     "szn_embed_argmax": [P, P, I, I, I, I, I, P, P, P],
     "szn_stitch_labels": [P, P, P, P, P, I, I, I, I, P, P],
     "szn_confusion_hist": [P, P, LL, I, P, P, P],
-    "szn_head_fused_fwd": [P, I, I, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
-    "szn_head_fused_bwd": [P, I, I, P, I, I, I, I, I, P, P, P, P, P],
+    "szn_head_fused_fwd": [I, P, I, I, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
+    "szn_head_fused_bwd": [I, P, I, I, P, I, I, I, I, I, P, P, P, P, P],
     "szn_sgd_step": [P, P, P, LL, ctypes.c_float, ctypes.c_float, ctypes.c_float, I, P],
     "szn_adam_step": [P, P, P, P, LL] + [ctypes.c_float] * 6 + [P],
 }

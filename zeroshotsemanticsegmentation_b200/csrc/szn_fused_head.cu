@@ -10,6 +10,8 @@
 //     dL/ds_k     = (g/N) [ sum_c M1[k,c] e_c/|e_c| + sum_l M2[k,l] s_l ]
 //                   M1[k,c] = sum_{p: t_p = c} w_k(p) a_p,  M2[k,l] = sum_p w_k(p) b_p w_l(p),
 //                   a_p = -1/|u_p|,  b_p = cos_p / |u_p|^2
+//   kind 1 (mse_loss, utils.py:50-73): |u_p - e_t|^2 = |u_p|^2 - 2 u_p.e_t + |e_t|^2 from the same quantities;
+//                   a_p = -2 (on the raw rows e_c), b_p = 2
 //
 // The algebra is pinned on the CPU by tools/fused_head_math.py + tests/test_fused_head_math.py (float64: loss 1e-10,
 // gradient 1e-8, labels exact against the materialised path).  Three small kernels replace four passes over 2.5 GB:
@@ -23,19 +25,20 @@ namespace szn {
 namespace {
 
 struct Ws {
-  float *en_inv, *A, *G, *M1, *M2;
+  float *en_inv, *en2, *A, *G, *M1, *M2;
 };
 
 __host__ __device__ inline long long ws_floats(int B, int hs, int ws, int C) {
   const long long K = (long long)hs * ws, cells = (long long)(hs + 1) * (ws + 1);
-  return C + B * K * C + B * K * 8 + B * cells * 4 * C + B * cells * 16;
+  return 2 * C + B * K * C + B * K * 8 + B * cells * 4 * C + B * cells * 16;
 }
 
 inline Ws carve(float* w, int B, int hs, int ws, int C) {
   const long long K = (long long)hs * ws, cells = (long long)(hs + 1) * (ws + 1);
   Ws r;
   r.en_inv = w;
-  r.A = r.en_inv + C;
+  r.en2 = r.en_inv + C;
+  r.A = r.en2 + C;
   r.G = r.A + B * K * C;
   r.M1 = r.G + B * K * 8;
   r.M2 = r.M1 + B * cells * 4 * C;
@@ -48,8 +51,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// en_inv[c] = 1 / |e_c|, 1 for zero rows (utils.py:175); one warp per class
-__global__ void fused_table_norm_kernel(const float* __restrict__ table, int C, int D, float* __restrict__ en_inv) {
+// en_inv[c] = 1 / |e_c|, 1 for zero rows (utils.py:175); en2[c] = |e_c|^2; one warp per class
+__global__ void fused_table_norm_kernel(const float* __restrict__ table, int C, int D, float* __restrict__ en_inv,
+                                        float* __restrict__ en2) {
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   float ss = 0.f;
@@ -58,7 +62,7 @@ __global__ void fused_table_norm_kernel(const float* __restrict__ table, int C, 
     ss = fmaf(v, v, ss);
   }
   ss = warp_sum(ss);
-  if (lane == 0) en_inv[c] = ss == 0.f ? 1.f : 1.f / sqrtf(ss);
+  if (lane == 0) en_inv[c] = ss == 0.f ? 1.f : 1.f / sqrtf(ss), en2[c] = ss;
 }
 
 // grid (hs*ws, B), block 128, dynamic smem 5*D floats.
@@ -93,17 +97,18 @@ __global__ void __launch_bounds__(128) fused_nodes_kernel(const float* __restric
 
 // grid (ws+1, hs+1, B): one CTA per tap neighbourhood ("cell", anchor node (ia, ja) = (blockIdx.y-1, blockIdx.x-1), taps
 // a = 2*da + db at node (ia+da, ja+db)); its pixels are the 32x32 block with y + 19 in [32(ia+1), 32(ia+1)+31].
-// block 256: thread = 4 consecutive x of one row.  dynamic smem: Ac[4*C] | einv[C] | M1w[8][4*C] | Gc[16] | M2w[8][16]
+// block 256: thread = 4 consecutive x of one row.  dynamic smem: Ac[4*C] | einv[C] | e2[C] | M1w[8][4*C] | Gc[16] | M2w[8][16]
 template <bool LOSS>
 __global__ void __launch_bounds__(256) fused_pixels_kernel(const float* __restrict__ A, const float* __restrict__ G,
-                                                           const float* __restrict__ en_inv,
-                                                           const long long* __restrict__ target, int H, int W, int hs, int ws,
-                                                           int C, float* __restrict__ M1, float* __restrict__ M2,
+                                                           const float* __restrict__ en_inv, const float* __restrict__ en2,
+                                                           int kind, const long long* __restrict__ target, int H, int W,
+                                                           int hs, int ws, int C, float* __restrict__ M1, float* __restrict__ M2,
                                                            double* __restrict__ accum, long long* __restrict__ labels) {
   extern __shared__ float sm[];
   float* Ac = sm;
   float* einv = Ac + 4 * C;
-  float* M1w = einv + C;
+  float* e2 = einv + C;
+  float* M1w = e2 + C;
   float* Gc = M1w + 8 * 4 * C;
   float* M2w = Gc + 16;
   __shared__ double red_a[8], red_b[8];
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(256) fused_pixels_kernel(const float* __restri
     const int a = idx / C, c = idx - a * C;
     Ac[idx] = ok[a] ? A[((long long)b * K + node[a]) * C + c] : 0.f;
   }
-  for (int c = tid; c < C; c += 256) einv[c] = en_inv[c];
+  for (int c = tid; c < C; c += 256) einv[c] = en_inv[c], e2[c] = en2[c];
   if (LOSS)
     for (int idx = tid; idx < 8 * 4 * C; idx += 256) M1w[idx] = 0.f;
   if (tid < 10) {
@@ -162,11 +167,17 @@ __global__ void __launch_bounds__(256) fused_pixels_kernel(const float* __restri
           const float un2 = w0 * w0 * Gc[0] + w1 * w1 * Gc[1] + w2 * w2 * Gc[2] + w3 * w3 * Gc[3] +
                             2.f * (w0 * w1 * Gc[4] + w2 * w3 * Gc[5] + w0 * w2 * Gc[6] + w1 * w3 * Gc[7] + w0 * w3 * Gc[8] +
                                    w1 * w2 * Gc[9]);
-          const float inv_un = rsqrtf(un2);
-          const float cs = pat * inv_un * einv[t];
-          part += cs;
+          float ap, bp;
+          if (kind == 0) {
+            const float inv_un = rsqrtf(un2);
+            const float cs = pat * inv_un * einv[t];
+            part += cs;
+            ap = -inv_un, bp = cs * inv_un * inv_un;
+          } else {
+            part += un2 - 2.f * pat + e2[t];
+            ap = -2.f, bp = 2.f;
+          }
           cnt += 1.0;
-          const float ap = -inv_un, bp = cs * inv_un * inv_un;
           float* m1 = M1w + warp * 4 * C + (int)t;
           atomicAdd(m1, w0 * ap);
           atomicAdd(m1 + C, w1 * ap);
@@ -232,8 +243,9 @@ __global__ void __launch_bounds__(256) fused_pixels_kernel(const float* __restri
 // ds[(b*K + k)*ld + ch]: ch in [coff, coff+D) = (gout / N) * gradient, 0 for every other channel of the row.
 __global__ void __launch_bounds__(128) fused_grad_kernel(const float* __restrict__ s17, int ld, int coff,
                                                          const float* __restrict__ table, const float* __restrict__ en_inv,
-                                                         int D, int hs, int ws, int C, const float* __restrict__ M1,
-                                                         const float* __restrict__ M2, const double* __restrict__ accum,
+                                                         int kind, int D, int hs, int ws, int C,
+                                                         const float* __restrict__ M1, const float* __restrict__ M2,
+                                                         const double* __restrict__ accum,
                                                          const float* __restrict__ gout, float* __restrict__ ds) {
   extern __shared__ float sm[];
   float* m1n = sm;
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(128) fused_grad_kernel(const float* __restrict
       const long long cell = (long long)(ia + 1) * (ws + 1) + (ja + 1);
       v += M1[((long long)b * cells + cell) * 4 * C + a * C + c];
     }
-    m1n[c] = v * en_inv[c];
+    m1n[c] = kind == 0 ? v * en_inv[c] : v;  // cosine: unit rows e_c/|e_c|; MSE: the rows themselves
   }
   if (tid < 16) {
     const int a = tid >> 2, a2 = tid & 3;
@@ -292,7 +304,7 @@ static int fused_common(const float* s17, int ld, int coff, const float* table, 
   if ((size_t)(8 * 4 * C + 5 * C + 160) * 4 > 200 * 1024 || (size_t)5 * D * 4 > 200 * 1024)
     return set_error(SZN_ERR_UNSUPPORTED, "szn_head_fused: C or D too large for the shared-memory tables");
   *out = carve(workspace, B, hs, ws, C);
-  fused_table_norm_kernel<<<(C + 3) / 4, 128, 0, st>>>(table, C, D, out->en_inv);
+  fused_table_norm_kernel<<<(C + 3) / 4, 128, 0, st>>>(table, C, D, out->en_inv, out->en2);
   if (int e = check_launch("szn_head_fused/norm")) return e;
   const size_t smem = (size_t)5 * D * sizeof(float);
   static size_t nodes_smem = 48 * 1024;
@@ -305,11 +317,11 @@ static int fused_common(const float* s17, int ld, int coff, const float* table, 
   return check_launch("szn_head_fused/nodes");
 }
 
-static size_t pixels_smem(int C) { return (size_t)(4 * C + C + 8 * 4 * C + 16 + 8 * 16) * sizeof(float); }
+static size_t pixels_smem(int C) { return (size_t)(4 * C + 2 * C + 8 * 4 * C + 16 + 8 * 16) * sizeof(float); }
 
 template <bool LOSS>
-static int launch_pixels(const Ws& w, const long long* target, int B, int H, int W, int hs, int ws, int C, double* accum,
-                         long long* labels, cudaStream_t st) {
+static int launch_pixels(const Ws& w, int kind, const long long* target, int B, int H, int W, int hs, int ws, int C,
+                         double* accum, long long* labels, cudaStream_t st) {
   const size_t smem = pixels_smem(C);
   static size_t cur = 48 * 1024;
   if (smem > cur) {
@@ -317,37 +329,38 @@ static int launch_pixels(const Ws& w, const long long* target, int B, int H, int
       return set_error(SZN_ERR_CUDA, "szn_head_fused: shared memory attribute");
     cur = smem;
   }
-  fused_pixels_kernel<LOSS><<<dim3(ws + 1, hs + 1, B), 256, smem, st>>>(w.A, w.G, w.en_inv, target, H, W, hs, ws, C, w.M1,
-                                                                       w.M2, accum, labels);
+  fused_pixels_kernel<LOSS><<<dim3(ws + 1, hs + 1, B), 256, smem, st>>>(w.A, w.G, w.en_inv, w.en2, kind, target, H, W, hs, ws,
+                                                                       C, w.M1, w.M2, accum, labels);
   return check_launch("szn_head_fused/pixels");
 }
 
-extern "C" int szn_head_fused_fwd(const float* s17, int ld, int coff, const long long* target, const float* table, int B,
-                                  int D, int H, int W, int hs, int ws, int C, float* workspace, double* accum, float* loss,
-                                  long long* labels, void* stream) {
+extern "C" int szn_head_fused_fwd(int kind, const float* s17, int ld, int coff, const long long* target, const float* table,
+                                  int B, int D, int H, int W, int hs, int ws, int C, float* workspace, double* accum,
+                                  float* loss, long long* labels, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // every output pixel must find its taps inside the (hs+1) x (ws+1) cell grid: y + 19 < 32 * (hs + 1)
   if (H + 19 > 32 * (hs + 1) || W + 19 > 32 * (ws + 1)) return set_error(SZN_ERR_ARG, "szn_head_fused_fwd: H/W vs hs/ws");
+  if (kind != 0 && kind != 1) return set_error(SZN_ERR_ARG, "szn_head_fused_fwd: kind");
   Ws w{};
   if (int e = fused_common(s17, ld, coff, table, B, D, hs, ws, C, workspace, &w, st)) return e;
   if (target) {
     if (!accum || !loss) return set_error(SZN_ERR_ARG, "szn_head_fused_fwd: accum / loss");
     cudaMemsetAsync(accum, 0, 2 * sizeof(double), st);
-    if (int e = launch_pixels<true>(w, target, B, H, W, hs, ws, C, accum, labels, st)) return e;
-    return szn_loss_finalize(0, accum, loss, stream);
+    if (int e = launch_pixels<true>(w, kind, target, B, H, W, hs, ws, C, accum, labels, st)) return e;
+    return szn_loss_finalize(kind, accum, loss, stream);
   }
   if (!labels) return set_error(SZN_ERR_ARG, "szn_head_fused_fwd: nothing to compute");
-  return launch_pixels<false>(w, nullptr, B, H, W, hs, ws, C, nullptr, labels, st);
+  return launch_pixels<false>(w, kind, nullptr, B, H, W, hs, ws, C, nullptr, labels, st);
 }
 
-extern "C" int szn_head_fused_bwd(const float* s17, int ld, int coff, const float* table, int B, int D, int hs, int ws,
-                                  int C, const float* workspace, const double* accum, const float* grad_out, float* ds17,
+extern "C" int szn_head_fused_bwd(int kind, const float* s17, int ld, int coff, const float* table, int B, int D, int hs,
+                                  int ws, int C, const float* workspace, const double* accum, const float* grad_out, float* ds17,
                                   void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (B < 1 || D < 1 || C < 1 || ld < coff + D) return set_error(SZN_ERR_ARG, "szn_head_fused_bwd: bad shape");
   const Ws w = carve(const_cast<float*>(workspace), B, hs, ws, C);
   const size_t smem = (size_t)(C + 16) * sizeof(float);
-  fused_grad_kernel<<<dim3(hs * ws, B), 128, smem, st>>>(s17, ld, coff, table, w.en_inv, D, hs, ws, C, w.M1, w.M2, accum,
+  fused_grad_kernel<<<dim3(hs * ws, B), 128, smem, st>>>(s17, ld, coff, table, w.en_inv, kind, D, hs, ws, C, w.M1, w.M2, accum,
                                                          grad_out, ds17);
   return check_launch("szn_head_fused_bwd");
 }

@@ -112,11 +112,11 @@ def _fused_workspace(s17, C):
 
 
 class _FusedHeadLoss(torch.autograd.Function):
-    """EXPERIMENTAL: ``cosine_loss`` on the hs x ws score map (``szn_head_fused_*``); input and gradient are
-    [B,hs,ws,Dp] fp32, the (B, D, H, W) score tensor is not touched."""
+    """EXPERIMENTAL: ``cosine_loss`` (kind 0) / ``mse_loss`` (kind 1) on the hs x ws score map (``szn_head_fused_*``);
+    input and gradient are [B,hs,ws,Dp] fp32, the (B, D, H, W) score tensor is not touched."""
 
     @staticmethod
-    def forward(ctx, s17, target, table, D, hw, accum_hook):
+    def forward(ctx, s17, target, table, D, hw, accum_hook, kind=0):
         _check_cuda(s17, target, table)
         B, hs, ws, ld = s17.shape
         H, W = hw
@@ -130,23 +130,23 @@ class _FusedHeadLoss(torch.autograd.Function):
         accum = torch.empty(2, device=sc.device, dtype=torch.float64)
         loss = torch.empty((), device=sc.device, dtype=torch.float32)
         st = _lib.stream()
-        call("szn_head_fused_fwd", ptr(sc), ld, 0, ptr(tg), ptr(tb), B, D, H, W, hs, ws, C, ptr(work), ptr(accum), ptr(loss),
-             None, st)
+        call("szn_head_fused_fwd", kind, ptr(sc), ld, 0, ptr(tg), ptr(tb), B, D, H, W, hs, ws, C, ptr(work), ptr(accum),
+             ptr(loss), None, st)
         if accum_hook is not None:
             accum_hook(accum)
-            call("szn_loss_finalize", 0, ptr(accum), ptr(loss), st)
-        ctx.saved = (sc, tb, work, accum, D)
+            call("szn_loss_finalize", kind, ptr(accum), ptr(loss), st)
+        ctx.saved = (sc, tb, work, accum, D, kind)
         return loss
 
     @staticmethod
     def backward(ctx, gout):
-        sc, tb, work, accum, D = ctx.saved
+        sc, tb, work, accum, D, kind = ctx.saved
         B, hs, ws, ld = sc.shape
         ds = torch.empty_like(sc)
         go = gout.detach().contiguous().float()
-        call("szn_head_fused_bwd", ptr(sc), ld, 0, ptr(tb), B, D, hs, ws, tb.shape[0], ptr(work), ptr(accum), ptr(go), ptr(ds),
-             _lib.stream())
-        return ds, None, None, None, None, None
+        call("szn_head_fused_bwd", kind, ptr(sc), ld, 0, ptr(tb), B, D, hs, ws, tb.shape[0], ptr(work), ptr(accum), ptr(go),
+             ptr(ds), _lib.stream())
+        return ds, None, None, None, None, None, None
 
 
 class _CrossEntropy2d(torch.autograd.Function):
@@ -188,6 +188,9 @@ def cross_entropy2d(score, target, weight=None, size_average=False, accum_hook=N
 
 def mse_loss(score, target, target_embed=None, table=None, accum_hook=None):
     """sum over valid pixels and channels of (score - target_embed)^2 / n_valid (``utils.py:50-73``)."""
+    head = _fused_handle(score) if target_embed is None and table is not None else None
+    if head is not None:  # experimental FCN32s(fused_head=True)
+        return _FusedHeadLoss.apply(head.s17, target, table, head.D, head.hw, accum_hook, 1)
     return _EmbedLoss.apply(score, target, target_embed, table, 1, accum_hook)
 
 
@@ -210,7 +213,7 @@ def _labels_device(score, embed_arr):
             raise ValueError("embedding width %d does not match score channels %d" % (tb.shape[1], c))
         out = torch.empty((n, h, w), device=score.device, dtype=torch.int64)
         work = _fused_workspace(s17, tb.shape[0])
-        call("szn_head_fused_fwd", ptr(s17), s17.shape[3], 0, None, ptr(tb), n, c, h, w, s17.shape[1], s17.shape[2],
+        call("szn_head_fused_fwd", 0, ptr(s17), s17.shape[3], 0, None, ptr(tb), n, c, h, w, s17.shape[1], s17.shape[2],
              tb.shape[0], ptr(work), None, None, ptr(out), _lib.stream())
         return out
     sc, tb = _as_f32(score), _as_f32(embed_arr)
