@@ -76,7 +76,7 @@ def test_fcn_trainer_forward_contract_and_parity(tmp_path):
         f, s = O.forward(data, params, "both")
     loss_ref = O.cosine_loss(f, target, O.target_embed_from_labels(target, tab))
     assert abs(loss.item() - loss_ref.item()) < 1e-4
-    assert agreement(lbl_pred, O.infer_lbl(f, tab)) > 0.999
+    assert agreement(lbl_pred, O.infer_lbl(f, tab)) > 0.995   # TF32 score vs fp32 oracle score: near-ties may move
     # a reference-style loader item (lbl, lbl_vec) gives the same loss as the on-device table gather
     _, loss2, _, _ = tr.forward(data, (target, O.target_embed_from_labels(target, tab)))
     assert abs(loss2.item() - loss.item()) < 1e-6
@@ -85,11 +85,11 @@ def test_fcn_trainer_forward_contract_and_parity(tmp_path):
     assert torch.equal(tr.seen_embeddings.cpu(), seen_tab) and torch.equal(tr.unseen_embeddings.cpu(), unseen_tab)
     tr.forced_unseen = True
     _, _, lp_forced, _ = tr.forward(data, target)
-    assert agreement(lp_forced, O.infer_lbl_forced_unseen(f, target, seen_tab, unseen_tab, UNSEEN)) > 0.999
+    assert agreement(lp_forced, O.infer_lbl_forced_unseen(f, target, seen_tab, unseen_tab, UNSEEN)) > 0.995
     tr.forced_unseen = False
     fs, loss3, lp_szn, lt3 = tr.forward_szn(data, target)
     assert abs(loss3.item() - loss_ref.item()) < 1e-4 and isinstance(lp_szn, np.ndarray)
-    assert agreement(lp_szn, O.infer_lbl_szn(f, s, seen_tab, unseen_tab)) > 0.995
+    assert agreement(lp_szn, O.infer_lbl_szn(f, s, seen_tab, unseen_tab)) > 0.99
 
 
 def nan_equal(a, b):
