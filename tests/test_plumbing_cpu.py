@@ -141,3 +141,73 @@ def test_optimizers_call_their_kernels_with_bound_signatures(stubbed, monkeypatc
         opt.step()
         assert p._version == v0 + 1                       # the packed-weight cache sees the update
     assert stubbed.names[-2:] == ["szn_sgd_step", "szn_adam_step"]
+
+
+class _Loader(list):
+    def __init__(self, batches, n_class=C):
+        super().__init__(batches)
+        import types
+        self.dataset = types.SimpleNamespace(class_names=["c%d" % i for i in range(n_class)])
+
+
+@pytest.fixture()
+def trainer_stubs(stubbed, monkeypatch):
+    from zeroshotsemanticsegmentation_b200 import optim, trainer
+    monkeypatch.setattr(optim, "call", stubbed)
+    monkeypatch.setattr(trainer, "_require_cuda", lambda device: None)
+    monkeypatch.setattr(trainer._Base, "_check_loss", staticmethod(lambda loss: 0.0))   # the stubbed loss is uninitialised memory
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))            # CPU tensors pass the device checks
+    return stubbed
+
+
+@pytest.mark.parametrize("loss_func,forced", [("cos", False), ("mse", True), ("cross_entropy", False)])
+def test_fcn_trainer_control_flow(trainer_stubs, tmp_path, loss_func, forced):
+    """trainer_fcn.py:83-158,181-292 through trainer.Trainer with stubbed kernels: all three losses, forced-unseen and
+    stitched inference, logs and checkpoint; the reference-style (lbl, lbl_vec) item and the labels-only item."""
+    import os
+    from zeroshotsemanticsegmentation_b200 import optim, trainer
+    emb = loss_func != "cross_entropy"
+    m = models.FCN32s(D if emb else C)
+    x, lab, table = inputs(2)
+    vec = table[lab.clamp(min=0)].permute(0, 3, 1, 2).contiguous()
+    batches = [(x, lab), (x, (lab, vec))] if emb else [(x, lab)]
+    ps = [p for n, p in m.named_parameters() if "upscore" not in n and not n.startswith("seenmask")]
+    tr = trainer.Trainer(True, m, optim.FusedSGD(ps, lr=1e-3, momentum=0.99), _Loader(batches), _Loader(batches),
+                         str(tmp_path), "pascal", 1, None, pixel_embeddings=D if emb else None, loss_func=loss_func,
+                         unseen=[1, 4], val_unseen=[4], forced_unseen=forced, embed_arr=table.numpy() if emb else None)
+    tr.verbose = False
+    tr.train()
+    assert tr.iteration == len(batches)
+    names = trainer_stubs.names
+    want_loss = "szn_ce2d_fwd" if loss_func == "cross_entropy" else "szn_embed_loss_fwd"
+    assert want_loss in names and "szn_sgd_step" in names and "szn_confusion_hist" in names
+    assert ("szn_stitch_labels" in names) == (emb and forced)
+    assert ("szn_embed_argmax" in names) == emb
+    assert os.path.isfile(os.path.join(str(tmp_path), "checkpoint")) and os.path.isfile(os.path.join(str(tmp_path), "val_log.csv"))
+    if emb:
+        del names[:]
+        tr.validate(both_fcn_and_seenmask=True)
+        assert "szn_stitch_labels" in names
+        score, loss, lbl_pred, lbl_true = tr.forward_szn(x, (lab, vec))
+        assert lbl_pred.shape == (2, H, W) and lbl_true.shape == (2, H, W)
+    else:
+        with pytest.raises(ValueError):
+            tr.forward_szn(x, lab)
+    with pytest.raises(ValueError):
+        trainer.Trainer(True, m, None, _Loader([]), _Loader([]), None, "pascal", 1, loss_func="bogus", n_class=C)
+
+
+def test_seenmask_trainer_control_flow(trainer_stubs, tmp_path):
+    from zeroshotsemanticsegmentation_b200 import optim, trainer
+    m = models.FCN32s(D)
+    x, lab, table = inputs(1)
+    head = trainer.freeze_for_seenmask(m)
+    tr = trainer.SeenmaskTrainer(True, m, optim.FusedAdam([{"params": head}], lr=1e-3), _Loader([(x, lab)]),
+                                 _Loader([(x, (lab, None))]), str(tmp_path), "pascal", 1, None, checkpoint={"epoch": 3},
+                                 unseen=[1, 4])
+    tr.verbose = False
+    tr.train()
+    names = trainer_stubs.names
+    assert names.count("szn_adam_step") == 3 and "szn_conv_dgrad" not in names and "szn_ce2d_bwd" in names
+    best = torch.load(str(tmp_path / "best"), weights_only=False)
+    assert best["epoch"] == 3 and "seenmask_score.weight" in best["model_state_dict"]

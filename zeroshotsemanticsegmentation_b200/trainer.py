@@ -97,6 +97,11 @@ def load_checkpoint(path, model, optimizer=None, map_location=None):
     return ckpt
 
 
+def _require_cuda(device):
+    if device.type != "cuda":
+        raise RuntimeError("move the model to the GPU before building a trainer (train.py:121-122)")
+
+
 class _Base(object):
     log_prefix = ""
     tb_prefix = "fcn"
@@ -122,8 +127,7 @@ class _Base(object):
         self.n_class = n_class
         self.timestamp_start = time.time()
         self.device = next(model.parameters()).device
-        if self.device.type != "cuda":
-            raise RuntimeError("move the model to the GPU before building a trainer (train.py:121-122)")
+        _require_cuda(self.device)
         self.verbose = True
         # data parallel (one process per GPU, ddp.GradientAllReduce attached to the model): the losses then normalise by
         # the valid-pixel count of the GLOBAL batch; gradients are all-reduced inside backward
@@ -253,12 +257,11 @@ class Trainer(_Base):
 
     # ---- the hot path, in the reference's call order (trainer_fcn.py:83-120) ----
     def _loss(self, score, target, target_embed):
-        table = None if target_embed is not None else self.embeddings
-        if self.loss_func == "cos":
-            return utils.cosine_loss(score, target, target_embed, table=table, accum_hook=self._accum_hook)
-        if self.loss_func == "mse":
-            return utils.mse_loss(score, target, target_embed, table=table, accum_hook=self._accum_hook)
-        return utils.cross_entropy2d(score, target, size_average=False, accum_hook=self._accum_hook)
+        if self.loss_func == "cross_entropy":
+            return utils.cross_entropy2d(score, target, size_average=False, accum_hook=self._accum_hook)
+        table = None if target_embed is not None else self.embeddings  # labels-only loader: gather E[label] on the device
+        fn = utils.cosine_loss if self.loss_func == "cos" else utils.mse_loss
+        return fn(score, target, target_embed, table=table, accum_hook=self._accum_hook)
 
     def _forward_device(self, data, target, szn=False):
         target, target_embed = self._split_target(target)
