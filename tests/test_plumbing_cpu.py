@@ -211,3 +211,57 @@ def test_seenmask_trainer_control_flow(trainer_stubs, tmp_path):
     assert names.count("szn_adam_step") == 3 and "szn_conv_dgrad" not in names and "szn_ce2d_bwd" in names
     best = torch.load(str(tmp_path / "best"), weights_only=False)
     assert best["epoch"] == 3 and "seenmask_score.weight" in best["model_state_dict"]
+
+
+def test_rare_engine_routes(stubbed, monkeypatch):
+    """Paths the benchmark never takes: the dense upscore weight gradient the reference computes and discards
+    (trainer_fcn.py:161-162), a trained (non-bilinear) upscore weight, bf16 storage, the data-parallel gradient hooks."""
+    x, lab, table = inputs(1)
+    # upscore_weight_grad=True: .grad of the (D,D,64,64) deconv weight is produced
+    m = models.FCN32s(D, upscore_weight_grad=True).eval()
+    f, s = run(m, x)
+    utils.mse_loss(f, lab, table=table).backward()
+    assert m.upscore.weight.grad is not None and m.upscore.weight.grad.shape == (D, D, 64, 64)
+    assert "szn_deconv_small_wgrad" in stubbed.names
+    # a trained upscore weight is no longer the frozen diagonal filter: dense small-deconv kernels on both passes
+    m = models.FCN32s(D).eval()
+    with torch.no_grad():
+        m.upscore.weight[0, 1, 3, 3] = 0.5
+    del stubbed.names[:]
+    f, s = run(m, x)
+    assert stubbed.names.count("szn_deconv_small_fwd") == 2 and "szn_upsample32_crop_fwd" not in stubbed.names
+    utils.cosine_loss(f, lab, table=table).backward()
+    assert "szn_deconv_small_dgrad" in stubbed.names and "szn_upsample32_crop_bwd" not in stubbed.names
+    # bf16 storage: activations are bf16 tensors, the public outputs stay fp32
+    m = models.FCN32s(D, precision="bf16").eval()
+    f, s = run(m, x)
+    assert f.dtype == torch.float32 and s.dtype == torch.float32
+    (f.sum() + s.sum()).backward()
+    assert m.conv2_1.weight.grad.dtype == torch.float32 and m.seenmask_upscore.weight.grad.shape == (2, 2, 64, 64)
+    # data-parallel hooks: every parameter gradient is announced exactly once, the flush comes last
+    m = models.FCN32s(D).eval()
+    seen, order = [], []
+    m._grad_ready = lambda name, g: (seen.append(name), order.append("g"))
+    m._grad_flush = lambda: order.append("flush")
+    f, s = run(m, x)
+    utils.cosine_loss(f, lab, table=table).backward()
+    expected = {n for n, p in m.named_parameters() if "upscore" not in n and not n.startswith("seenmask")}
+    assert sorted(seen) == sorted(expected) and order[-1] == "flush" and order.count("flush") == 1
+    assert seen[0].startswith("score_fr") and seen.index("fc6.weight") < seen.index("conv1_1.weight")  # fc6's 411 MB go first
+
+
+def test_inference_helpers_return_numpy_like_the_reference(stubbed):
+    x, lab, table = inputs(2)
+    score = torch.randn(2, D, H, W)
+    sm = torch.randn(2, 2, H, W)
+    seen_t, unseen_t = utils.split_embeddings(table, [1, 4])
+    import numpy as np
+    for out in (utils.infer_lbl(score, table), utils.infer_lbl_szn(score, sm, seen_t, unseen_t),
+                utils.infer_lbl_forced_unseen(score, lab, seen_t, unseen_t, [1, 4]),
+                utils.stich_seen_unseen_with_mask(score, seen_t, unseen_t, np.zeros((2, H, W), dtype=bool))):
+        assert isinstance(out, np.ndarray) and out.dtype == np.int64 and out.shape == (2, H, W)
+    assert stubbed.names.count("szn_stitch_labels") == 2 and stubbed.names.count("szn_embed_argmax") == 7
+    with pytest.raises(ValueError):
+        utils.infer_lbl(score, torch.zeros(C, D + 1))
+    with pytest.raises(NotImplementedError):
+        utils.cross_entropy2d(score, lab, weight=torch.ones(D))
