@@ -60,7 +60,8 @@ def test_module_surface_matches_reference():
     vgg.classifier = nn.Sequential(nn.Linear(25088, 4096), nn.ReLU(), nn.Dropout(), nn.Linear(4096, 4096))
     m.copy_params_from_vgg16(vgg)
     assert torch.equal(m.conv3_2.weight, vgg.features[7].weight)
-    assert torch.equal(m.fc6.weight.view(4096, -1), vgg.classifier[0].weight)
+    assert torch.equal(m.fc6.weight.reshape(4096, -1), vgg.classifier[0].weight)
+    assert m.fc6.weight.is_contiguous(memory_format=torch.channels_last)  # back in the layout the wgrad kernel writes
 
 
 def test_host_metrics_equal_live_reference():

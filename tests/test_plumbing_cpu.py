@@ -265,3 +265,18 @@ def test_inference_helpers_return_numpy_like_the_reference(stubbed):
         utils.infer_lbl(score, torch.zeros(C, D + 1))
     with pytest.raises(NotImplementedError):
         utils.cross_entropy2d(score, lab, weight=torch.ones(D))
+
+
+def test_engine_rejects_what_the_kernels_cannot_read(stubbed):
+    m = models.FCN32s(D).eval()
+    x, _, _ = inputs(1)
+    with pytest.raises(TypeError):
+        run(m, x.double())
+    with pytest.raises(ValueError):
+        run(m, torch.zeros(1, 4, H, W))
+    with pytest.raises(NotImplementedError):
+        run(m, x.clone().requires_grad_(True))
+    m.fc7.double()
+    with pytest.raises(TypeError, match="fc7.weight"):
+        run(m, x)
+    assert stubbed.names == []   # nothing was launched

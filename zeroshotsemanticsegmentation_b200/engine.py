@@ -138,6 +138,15 @@ class FCN32sFunction(torch.autograd.Function):
         dev = x.device
         if x.dtype != torch.float32:
             raise TypeError("FCN32s expects an fp32 image batch")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("FCN32s expects a (B, 3, H, W) image batch, got %s" % (tuple(x.shape),))
+        if x.requires_grad:
+            raise NotImplementedError("the gradient with respect to the image is not computed (conv1_1 has no dgrad)")
+        for name, prm in zip(PARAM_ORDER, params):
+            # the kernels read raw fp32 storage on the input's device: anything else would be read as garbage
+            if prm.dtype != torch.float32 or prm.device != dev:
+                raise TypeError("parameter %s is %s on %s; the B200 path needs fp32 parameters on the input's device (%s)"
+                                % (name, prm.dtype, prm.device, dev))
         x = x.contiguous()
         B, _, H, W = x.shape
         P = dict(zip(PARAM_ORDER, params))

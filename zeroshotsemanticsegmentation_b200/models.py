@@ -128,3 +128,4 @@ class FCN32s(nn.Module):
             src, dst = vgg16.classifier[i], getattr(self, name)
             dst.weight.data = src.weight.data.view(dst.weight.size())
             dst.bias.data = src.bias.data.view(dst.bias.size())
+        self._use_kernel_weight_layout()  # the copied tensors are NCHW-dense: back to the layout the wgrad kernel writes
