@@ -280,3 +280,26 @@ def test_engine_rejects_what_the_kernels_cannot_read(stubbed):
     with pytest.raises(TypeError, match="fc7.weight"):
         run(m, x)
     assert stubbed.names == []   # nothing was launched
+
+
+def test_losses_and_labels_reject_mismatched_shapes(stubbed):
+    """The kernels index raw memory; a wrong shape must raise before anything is launched (the reference raises inside
+    torch for the same mistakes)."""
+    score = torch.randn(2, D, H, W)
+    lab = torch.zeros(2, H, W, dtype=torch.long)
+    table = torch.randn(C, D)
+    bad = [lambda: utils.cosine_loss(score, lab[:1], table=table),
+           lambda: utils.cosine_loss(score, lab, torch.zeros(2, D, H, W + 1)),
+           lambda: utils.mse_loss(score, lab, table=torch.randn(C, D + 1)),
+           lambda: utils.mse_loss(score, lab),
+           lambda: utils.cross_entropy2d(score, lab[:, :-1]),
+           lambda: utils.cross_entropy2d(score[0], lab),
+           lambda: utils.infer_lbl(score, torch.randn(C, D - 1)),
+           lambda: utils.infer_lbl_szn(score, torch.zeros(2, 3, H, W), table, table),
+           lambda: utils.infer_lbl_forced_unseen(score, lab[:1], table, table, [1]),
+           lambda: utils.confusion_hist_device(lab, lab[:1], C)]
+    for fn in bad:
+        with pytest.raises(ValueError):
+            fn()
+    assert "szn_embed_loss_fwd" not in stubbed.names and "szn_ce2d_fwd" not in stubbed.names
+    assert "szn_stitch_labels" not in stubbed.names and "szn_confusion_hist" not in stubbed.names

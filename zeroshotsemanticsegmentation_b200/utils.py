@@ -67,10 +67,26 @@ def _as_f32(t):
     return t.detach().contiguous().float() if t is not None else None
 
 
+def _check_shapes(score, target, target_embed=None, table=None):
+    """The kernels index raw memory: reject shapes that would read out of bounds before anything is launched."""
+    if score.dim() != 4:
+        raise ValueError("score must be (n, c, h, w), got %s" % (tuple(score.shape),))
+    n, c, h, w = score.shape
+    if target is not None and tuple(target.shape) != (n, h, w):
+        raise ValueError("target must be (n, h, w) = %s, got %s" % ((n, h, w), tuple(target.shape)))
+    if target_embed is not None and tuple(target_embed.shape) != (n, c, h, w):
+        raise ValueError("target_embed must have the score's shape %s, got %s" % ((n, c, h, w), tuple(target_embed.shape)))
+    if table is not None and (table.dim() != 2 or table.shape[1] != c):
+        raise ValueError("the class table must be (C, %d), got %s" % (c, tuple(table.shape)))
+
+
 class _EmbedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, score, target, target_embed, table, kind, accum_hook):
         _check_cuda(score, target, target_embed, table)
+        _check_shapes(score, target, target_embed, table)
+        if target_embed is None and table is None:
+            raise ValueError("give either target_embed (n,c,h,w) or table (C,c) to gather it from")
         n, c, h, w = score.shape
         sc = _as_f32(score)
         tg = target.detach().contiguous().long()
@@ -153,6 +169,7 @@ class _CrossEntropy2d(torch.autograd.Function):
     @staticmethod
     def forward(ctx, score, target, size_average, accum_hook):
         _check_cuda(score, target)
+        _check_shapes(score, target)
         n, c, h, w = score.shape
         sc = _as_f32(score)
         tg = target.detach().contiguous().long()
@@ -204,6 +221,7 @@ def cosine_loss(score, target, target_embed=None, table=None, accum_hook=None):
 
 def _labels_device(score, embed_arr):
     _check_cuda(score, embed_arr)
+    _check_shapes(score, None, None, embed_arr)
     n, c, h, w = score.shape
     head = _fused_handle(score)
     if head is not None:  # experimental FCN32s(fused_head=True)
@@ -241,6 +259,10 @@ def _stitch(score, seen_embed_arr, unseen_embed_arr, seen_mask_score=None, targe
     seen_lbl = _labels_device(score, seen_embed_arr)
     unseen_lbl = _labels_device(score, unseen_embed_arr)
     n, h, w = seen_lbl.shape
+    if seen_mask_score is not None and tuple(seen_mask_score.shape) != (n, 2, h, w):
+        raise ValueError("seen_mask_score must be (n, 2, h, w) = %s, got %s" % ((n, 2, h, w), tuple(seen_mask_score.shape)))
+    if target is not None and tuple(target.shape) != (n, h, w):
+        raise ValueError("target must be (n, h, w) = %s, got %s" % ((n, h, w), tuple(target.shape)))
     out = torch.empty_like(seen_lbl)
     sm = _as_f32(seen_mask_score)
     tg = target.detach().contiguous().long() if target is not None else None
@@ -319,6 +341,8 @@ def confusion_hist_device(label_true, label_pred, n_class, unseen=None):
     """Confusion matrices of ``_fast_hist`` (``utils.py:104-121``) for CUDA label tensors, built on the device.
     Returns an int64 CUDA tensor (1 or 3, n_class, n_class): target 'all' [, 'seen', 'unseen']."""
     _check_cuda(label_true, label_pred)
+    if label_true.numel() != label_pred.numel():
+        raise ValueError("label_true and label_pred differ in size: %s vs %s" % (tuple(label_true.shape), tuple(label_pred.shape)))
     lt = label_true.detach().contiguous().long().view(-1)
     lp = label_pred.detach().contiguous().long().view(-1)
     flags = None
