@@ -271,17 +271,17 @@ class Trainer(_Base):
         else:
             score = self.model(data, mode="fcn")  # trainer_fcn.py:97
         loss = self._loss(score, target, target_embed)
-        sc = score.detach()
+        # the label functions detach internally; the score itself is passed on so that a fused-head handle survives
         if szn:
-            lbl_pred = utils.infer_lbl_szn_device(sc, seen_mask_score.detach(), self.seen_embeddings,
+            lbl_pred = utils.infer_lbl_szn_device(score, seen_mask_score.detach(), self.seen_embeddings,
                                                   self.unseen_embeddings)
         elif self.pixel_embeddings and self.forced_unseen:
-            lbl_pred = utils.infer_lbl_forced_unseen_device(sc, target, self.seen_embeddings, self.unseen_embeddings,
+            lbl_pred = utils.infer_lbl_forced_unseen_device(score, target, self.seen_embeddings, self.unseen_embeddings,
                                                             self.unseen)
         elif self.pixel_embeddings:
-            lbl_pred = utils.infer_lbl_device(sc, self.embeddings)
+            lbl_pred = utils.infer_lbl_device(score, self.embeddings)
         else:
-            lbl_pred = sc.max(1)[1]
+            lbl_pred = score.detach().max(1)[1]
         return score, loss, lbl_pred, target
 
     def forward(self, data, target):
