@@ -17,7 +17,7 @@
 using namespace szn;
 
 struct Cfg {
-  int tf32, M, N, nacc, iters;
+  int tf32, M, N, nacc, iters, issue;
 };
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(Cfg c, long long* cycles_out) {
@@ -42,24 +42,40 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Cfg c, long long* cycles_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tptr;
-  if (threadIdx.x == 0) {
-    const uint32_t idesc = umma_idesc(c.tf32 ? 2 : 1, 0, 0, c.M, c.N);
-    const uint32_t a_base = smem_u32(smem), b_base = a_base + STAGES * A_BYTES;
-    const int acc_cols = c.N < 32 ? 32 : c.N;
-    const long long t0 = clock64();
-    for (int it = 0; it < c.iters; ++it) {
-      const int s = it & (STAGES - 1), k = (it >> 2) & 3, acc = it % c.nacc;
-      const uint64_t ad = umma_desc_sw128(a_base + s * A_BYTES + k * 32, 16, 1024);
-      const uint64_t bd = umma_desc_sw128(b_base + s * B_BYTES + k * 32, 16, 1024);
-      if (c.tf32)
-        tc_mma<true>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
-      else
-        tc_mma<false>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
+  // issue == 0: `if (threadIdx.x == 0)` (round-1 style: ptxas wraps every UTCHMMA in an ELECT/BRA.U.ANY loop)
+  // issue == 1: whole warp in the branch, one elected lane issues (what the kernels do now)
+  const uint32_t idesc = umma_idesc(c.tf32 ? 2 : 1, 0, 0, c.M, c.N);
+  const uint32_t a_base = smem_u32(smem), b_base = a_base + STAGES * A_BYTES;
+  const int acc_cols = c.N < 32 ? 32 : c.N;
+  if (c.issue == 0) {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      for (int it = 0; it < c.iters; ++it) {
+        const int s = it & (STAGES - 1), k = (it >> 2) & 3, acc = it & (c.nacc - 1);
+        const uint64_t ad = umma_desc_sw128(a_base + s * A_BYTES + k * 32, 16, 1024);
+        const uint64_t bd = umma_desc_sw128(b_base + s * B_BYTES + k * 32, 16, 1024);
+        if (c.tf32) tc_mma<true>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
+        else tc_mma<false>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
+      }
+      tc_commit(bar);
+      mbar_wait(bar, 0);
+      cycles_out[blockIdx.x] = clock64() - t0;
     }
-    tc_commit(bar);
+  } else if (warp_idx() == 0) {
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int it = 0; it < c.iters; ++it) {
+        const int s = it & (STAGES - 1), k = (it >> 2) & 3, acc = it & (c.nacc - 1);
+        const uint64_t ad = umma_desc_sw128(a_base + s * A_BYTES + k * 32, 16, 1024);
+        const uint64_t bd = umma_desc_sw128(b_base + s * B_BYTES + k * 32, 16, 1024);
+        if (c.tf32) tc_mma<true>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
+        else tc_mma<false>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
+      }
+      tc_commit(bar);
+    }
+    __syncwarp();
     mbar_wait(bar, 0);
-    const long long t1 = clock64();
-    cycles_out[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) cycles_out[blockIdx.x] = clock64() - t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -82,11 +98,13 @@ int main() {
   printf("device %d: %d SMs, nominal %.0f MHz\n", dev, sms, khz / 1000.0);
   printf("%-5s %4s %4s %5s | %10s | %10s | %s\n", "kind", "M", "N", "nacc", "cyc/MMA", "MAC/cyc/SM", "of the 1x-rate floor max(M,128)*N/256");
   const int Ms[2] = {128, 64}, Ns[5] = {32, 64, 128, 192, 256}, accs[3] = {1, 2, 4};
+  for (int issue = 0; issue < 2; ++issue)
   for (int tf32 = 1; tf32 >= 0; --tf32)
-    for (int mi = 0; mi < 2; ++mi)
+    for (int mi = 0; mi < (issue ? 2 : 1); ++mi)
       for (int ni = 0; ni < 5; ++ni)
         for (int ai = 0; ai < 3; ++ai) {
-          Cfg c{tf32, Ms[mi], Ns[ni], accs[ai], 4096};
+          if (!issue && (ai || (ni != 1 && ni != 4))) continue;  // the old issue style: two reference lines only
+          Cfg c{tf32, Ms[mi], Ns[ni], accs[ai], 4096, issue};
           const int acc_cols = c.N < 32 ? 32 : c.N;
           if (c.nacc * acc_cols > 512) continue;
           for (int rep = 0; rep < 2; ++rep) {  // first launch warms up
@@ -104,8 +122,8 @@ int main() {
           const double cyc = (double)worst / c.iters;
           const int kk = tf32 ? 8 : 16;
           const double floor_c = (double)(c.M > 128 ? c.M : 128) * c.N / 256.0;
-          printf("%-5s %4d %4d %5d | %10.1f | %10.0f | %.2fx\n", tf32 ? "tf32" : "bf16", c.M, c.N, c.nacc, cyc,
-                 (double)c.M * c.N * kk / cyc, cyc / floor_c);
+          printf("%-5s %4d %4d %5d | %10.1f | %10.0f | %.2fx%s\n", tf32 ? "tf32" : "bf16", c.M, c.N, c.nacc, cyc,
+                 (double)c.M * c.N * kk / cyc, cyc / floor_c, issue ? "" : "   [threadIdx.x == 0 issue]");
         }
   cudaFree(d);
   free(h);

@@ -66,7 +66,7 @@ embed_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_con
   uint64_t* accf = empty + 8;
   uint64_t* acce = accf + 2;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(acce + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx(), lane = threadIdx.x & 31;  // provably warp-uniform (see elect_one)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmS);
@@ -95,8 +95,8 @@ embed_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_con
   const uint32_t tmem = *tptr;
   const uint32_t buf_cols = (uint32_t)(p.nacc * p.acc_cols);  // hh | hl | lh, or (Cpad = 256) hh | hl + lh
 
-  if (warp == 0 && lane == 0) {
-    // ---------------- TMA producer ----------------
+  if (warp == 0) {
+    // ---------------- TMA producer (whole warp loops, one elected lane issues) ----------------
     int s = 0;
     uint32_t ph = 0;
     const uint32_t tx = (uint32_t)(A_BYTES + 2 * b_bytes);
@@ -104,16 +104,19 @@ embed_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_con
       const int b = tile / p.tiles_per_img, g0 = (tile - b * p.tiles_per_img) * 4;
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t* st = smem + s * stage_bytes;
-        mbar_expect_tx(&full[s], tx);
-        tma_load_4d(st, &tmS, &full[s], 0, kc * 32, b, g0);
-        tma_load_2d(st + 2 * A_BYTES, &tmHi, &full[s], kc * 32, 0);
-        tma_load_2d(st + 2 * A_BYTES + b_bytes, &tmLo, &full[s], kc * 32, 0);
+        if (elect_one()) {
+          uint8_t* st = smem + s * stage_bytes;
+          mbar_expect_tx(&full[s], tx);
+          tma_load_4d(st, &tmS, &full[s], 0, kc * 32, b, g0);
+          tma_load_2d(st + 2 * A_BYTES, &tmHi, &full[s], kc * 32, 0);
+          tma_load_2d(st + 2 * A_BYTES + b_bytes, &tmLo, &full[s], kc * 32, 0);
+        }
+        __syncwarp();
         if (++s == stages) s = 0, ph ^= 1u;
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ---------------- MMA issuer ----------------
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (whole warp loops, one elected lane issues) ----------------
     const uint32_t idesc = umma_idesc(2, 1, 0, 128, p.Cpad);  // tf32, A MN-major, B K-major
     const uint32_t idesc2 = umma_idesc(2, 1, 0, 128, 2 * p.Cpad);
     int s = 0;
@@ -128,6 +131,7 @@ embed_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_con
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(&split[s], ph);
         tc_fence_after();
+        if (elect_one()) {
         const uint32_t a_hi = smem_u32(smem + s * stage_bytes), a_lo = a_hi + A_BYTES;
         const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + (uint32_t)b_bytes;
 #pragma unroll
@@ -140,7 +144,7 @@ embed_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_con
           const uint64_t bl = umma_desc_sw128(b_lo + k * 32, 16, 1024);
           const uint32_t acc = (uint32_t)((kc | k) != 0);
           // B_hi and B_lo are stacked along N, so A_hi x [B_hi; B_lo] yields the hi*hi and hi*lo partial sums with ONE
-          // instruction (an N <= 256 MMA costs about the same ~130 cycles whatever N is); lo*hi is the second one.
+          // instruction (fewer instructions for the same MACs); lo*hi is the second one.
           if (p.nacc == 3) {
             tc_mma<true>(d0, ah, bh, idesc2, acc);                              // columns [0, 2*Cpad): hh | hl
             tc_mma<true>(d0 + 2u * (uint32_t)p.acc_cols, al, bh, idesc, acc);  // columns [2*Cpad, 3*Cpad): lh
@@ -153,9 +157,12 @@ embed_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_con
           }
         }
         tc_commit(&empty[s]);
+        }
+        __syncwarp();
         if (++s == stages) s = 0, ph ^= 1u;
       }
-      tc_commit(&accf[buf]);
+      if (elect_one()) tc_commit(&accf[buf]);
+      __syncwarp();
     }
   } else if (warp >= 2 && warp < 6) {
     // ---------------- operand split: A -> (hi in place, lo) ----------------

@@ -105,42 +105,53 @@ __global__ void __launch_bounds__(128) upsample_fwd_kernel(const float* __restri
 // thread): a row feeds source row iy1 with weight f(ky) and iy1-1 with f(ky+32); when a 32-row group ends, the finished
 // column sums are folded along x by 8 threads per ix (64 taps each).
 // VEC = 4: a thread owns 4 adjacent columns and reads 16 bytes per row (W % 4 == 0); VEC = 1: any W.
-template <typename T, int VEC>
+// NS column slots per thread (slot j = columns (threadIdx.x + j * blockDim.x) * VEC ...), so W <= blockDim.x * VEC * NS:
+// native-size PASCAL images (e.g. 500 x 375, train.py:82-84 feeds them unpadded at batch size 1) take VEC = 1, NS = 2.
+template <typename T, int VEC, int NS>
 __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ g, T* __restrict__ ds, int B, int D,
                                                            int H, int W, int hs, int ws, int ld, int coff) {
   extern __shared__ float col[];  // [W]
   const int plane = blockIdx.x;
   const int b = plane / D, d = plane - b * D;
   const float* gp = g + (long long)plane * H * W;
-  const int X0 = threadIdx.x * VEC;  // W <= 256 * VEC
-  const bool live = X0 < W;
-  float carry[VEC], accA[VEC], accB[VEC];
+  float carry[NS][VEC], accA[NS][VEC], accB[NS][VEC];
 #pragma unroll
-  for (int c = 0; c < VEC; ++c) carry[c] = accA[c] = accB[c] = 0.f;
+  for (int j = 0; j < NS; ++j)
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) carry[j][c] = accA[j][c] = accB[j][c] = 0.f;
   const int n_groups = (H + UPCROP + 31) >> 5;  // groups of rows with the same iy1 = (Y + 19) >> 5
   for (int k = 0; k <= n_groups; ++k) {
-    if (k < n_groups && live) {  // rows of group k: u = Y + 19 in [32k, 32k + 31]
+    if (k < n_groups) {  // rows of group k: u = Y + 19 in [32k, 32k + 31]
       int y0 = 32 * k - UPCROP, y1 = y0 + 32;
       if (y0 < 0) y0 = 0;
       if (y1 > H) y1 = H;
-#pragma unroll 8
-      for (int Y = y0; Y < y1; ++Y) {
-        const int ky = (Y + UPCROP) & 31;
-        const float fy1 = tent(ky), fy0 = tent(ky + 32);
-        const PixVec<VEC> v = ld_pix<VEC>(gp + (long long)Y * W + X0);
 #pragma unroll
-        for (int c = 0; c < VEC; ++c) {
-          accA[c] = fmaf(v.v[c], fy1, accA[c]);
-          accB[c] = fmaf(v.v[c], fy0, accB[c]);
+      for (int j = 0; j < NS; ++j) {
+        const int X0 = (threadIdx.x + j * blockDim.x) * VEC;
+        if (X0 >= W) continue;
+#pragma unroll 8
+        for (int Y = y0; Y < y1; ++Y) {
+          const int ky = (Y + UPCROP) & 31;
+          const float fy1 = tent(ky), fy0 = tent(ky + 32);
+          const PixVec<VEC> v = ld_pix<VEC>(gp + (long long)Y * W + X0);
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) {
+            accA[j][c] = fmaf(v.v[c], fy1, accA[j][c]);
+            accB[j][c] = fmaf(v.v[c], fy0, accB[j][c]);
+          }
         }
       }
     }
     // source row iy = k - 1 is complete: carry (its f(ky) part from group k-1) + accB (its f(ky+32) part from group k)
     const int iy = k - 1;
     if (iy >= 0 && iy < hs) {
-      if (live) {
 #pragma unroll
-        for (int c = 0; c < VEC; ++c) col[X0 + c] = carry[c] + accB[c];
+      for (int j = 0; j < NS; ++j) {
+        const int X0 = (threadIdx.x + j * blockDim.x) * VEC;
+        if (X0 < W) {
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) col[X0 + c] = carry[j][c] + accB[j][c];
+        }
       }
       __syncthreads();
       const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7, ngrp = blockDim.x >> 3;  // groups of 8 threads
@@ -161,7 +172,9 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
       __syncthreads();
     }
 #pragma unroll
-    for (int c = 0; c < VEC; ++c) carry[c] = accA[c], accA[c] = 0.f, accB[c] = 0.f;
+    for (int j = 0; j < NS; ++j)
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) carry[j][c] = accA[j][c], accA[j][c] = 0.f, accB[j][c] = 0.f;
   }
 }
 
@@ -612,21 +625,31 @@ extern "C" int szn_upsample32_crop_fwd(const float* s, float* out, int B, int D,
   return check_launch("szn_upsample32_crop_fwd");
 }
 
-extern "C" int szn_upsample32_crop_bwd(int dtype, const float* g, void* ds, int B, int D, int H, int W, int hs, int ws,
-                                       int ld, int coff, void* stream) {
+template <typename T>
+static void launch_upsample_bwd(const float* g, T* ds, int B, int D, int H, int W, int hs, int ws, int ld, int coff,
+                                bool v4, cudaStream_t st) {
   const unsigned grid = (unsigned)((long long)B * D);
   const size_t smem = (size_t)W * sizeof(float);
-  const bool v4 = W % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
-  if (W > (v4 ? 1024 : 256)) return set_error(SZN_ERR_UNSUPPORTED, "szn_upsample32_crop_bwd: W too large");
-  const int threads = v4 ? ((W / 4 + 31) / 32 * 32 < 64 ? 64 : (W / 4 + 31) / 32 * 32) : 256;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == SZN_BF16) {
-    if (v4) upsample_bwd_kernel<__nv_bfloat16, 4><<<grid, threads, smem, st>>>(g, (__nv_bfloat16*)ds, B, D, H, W, hs, ws, ld, coff);
-    else upsample_bwd_kernel<__nv_bfloat16, 1><<<grid, threads, smem, st>>>(g, (__nv_bfloat16*)ds, B, D, H, W, hs, ws, ld, coff);
+  if (v4) {
+    int threads = (W / 4 + 31) / 32 * 32;
+    if (threads < 64) threads = 64;
+    upsample_bwd_kernel<T, 4, 1><<<grid, threads, smem, st>>>(g, ds, B, D, H, W, hs, ws, ld, coff);
+  } else if (W <= 256) {
+    upsample_bwd_kernel<T, 1, 1><<<grid, 256, smem, st>>>(g, ds, B, D, H, W, hs, ws, ld, coff);
+  } else if (W <= 512) {
+    upsample_bwd_kernel<T, 1, 2><<<grid, 256, smem, st>>>(g, ds, B, D, H, W, hs, ws, ld, coff);
   } else {
-    if (v4) upsample_bwd_kernel<float, 4><<<grid, threads, smem, st>>>(g, (float*)ds, B, D, H, W, hs, ws, ld, coff);
-    else upsample_bwd_kernel<float, 1><<<grid, threads, smem, st>>>(g, (float*)ds, B, D, H, W, hs, ws, ld, coff);
+    upsample_bwd_kernel<T, 1, 4><<<grid, 256, smem, st>>>(g, ds, B, D, H, W, hs, ws, ld, coff);
   }
+}
+
+extern "C" int szn_upsample32_crop_bwd(int dtype, const float* g, void* ds, int B, int D, int H, int W, int hs, int ws,
+                                       int ld, int coff, void* stream) {
+  const bool v4 = W % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+  if (W > 1024) return set_error(SZN_ERR_UNSUPPORTED, "szn_upsample32_crop_bwd: W > 1024");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SZN_BF16) launch_upsample_bwd<__nv_bfloat16>(g, (__nv_bfloat16*)ds, B, D, H, W, hs, ws, ld, coff, v4, st);
+  else launch_upsample_bwd<float>(g, (float*)ds, B, D, H, W, hs, ws, ld, coff, v4, st);
   return check_launch("szn_upsample32_crop_bwd");
 }
 

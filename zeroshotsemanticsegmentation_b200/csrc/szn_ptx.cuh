@@ -49,6 +49,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a fully converged warp.  Single-thread roles (TMA producer, tcgen05.mma issuer) must be written as
+//   if (warp_uniform_idx == ROLE) { ...all 32 lanes loop and wait...  if (elect_one()) { issue } }
+// with the warp index made provably uniform (warp_idx()): under `if (threadIdx.x == k)` ptxas cannot prove that the
+// operands of UTCHMMA / UTMALDG (uniform-datapath instructions) are warp-uniform and wraps EVERY one of them in an
+// ELECT ... BRA.U.ANY serialisation loop whose scoreboard round trip costs ~140-190 cycles per instruction (measured
+// with tools/probe_mma.cu: 186 cycles per tcgen05.mma whatever its shape) -- the "per-instruction floor" of round 1.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ----------------------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");

@@ -22,8 +22,6 @@
 // descriptors, fp32 accumulators in TMEM (two buffers: the epilogue of a tile overlaps the next main loop).
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
 // (TMEM -> registers -> swizzled staging rows -> TMA store / reduce-add).  192 threads, one CTA per SM.
-// Debug hooks (never set in production): SZN_DBG / SZN_DBG_MODE skip operand loads or stores for timing
-// experiments, SZN_TRACE records clock64 stamps of CTA 0's roles (tools/trace_tiles.py).
 #include "szn_internal.h"
 #include "szn_ptx.cuh"
 #include <stdlib.h>
@@ -47,7 +45,6 @@ struct UmmaParams {
   int nbuf;   // accumulator buffers in TMEM (2 unless one tile needs all 512 columns)
   int nacc, acc_cols;  // accumulators per tile (K steps round-robin over them) and their TMEM column stride
   int gpt, b_boxes, ksteps;  // MODE 2: 128-byte column groups per B box, B boxes per stage, MMAs (K steps) per stage
-  int dbg;  // timing experiments only (SZN_DBG / SZN_DBG_MODE env): bit0 skip A loads, bit1 skip B loads
   long long ldo;          // row stride of the output, elements (mask_ref shares it)
   const float* bias;      // [N] or null
   const float* scale;     // [B][scale_ld] per-(image, channel) multiplier (Dropout2d) or null
@@ -57,7 +54,6 @@ struct UmmaParams {
   int relu, out_fp32;
   int vec_ok;  // bias / scale rows are 16-byte aligned
   float* col_sum;  // dgrad: += column sums of the stored output (the producer layer's bias gradient) or null
-  long long* trace;  // debug (SZN_TRACE): clock64 stamps of CTA 0's roles, [role][tile][4]
 };
 
 template <typename T>
@@ -161,7 +157,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* acce = accf + 2;   // [2] accumulator buffer drained
   uint32_t* tptr = reinterpret_cast<uint32_t*>(acce + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx(), lane = threadIdx.x & 31;  // provably warp-uniform (see elect_one)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -191,10 +187,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int rows_a = p.TW * p.TH;  // rows written by one pixel box
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // =========================== TMA producer ===========================
-    // One thread; all index decompositions inside a tile are carried incrementally (a runtime integer division costs
-    // ~100 cycles; 19 of them per wgrad stage made the producer the bottleneck in the first profile).
+    // The whole warp walks the loop (uniform control flow); one elected lane issues.  All index decompositions inside a
+    // tile are carried incrementally (a runtime integer division costs ~100 cycles; 19 of them per wgrad stage made the
+    // producer the bottleneck in the first profile).
     // MODE 2 operands are fetched with 5-D boxes {KC channels, TW, TH, 1, G channel groups}: one box lands G column
     // groups (each rows_a x 128 B, back to back) instead of one 4 KB box per group -- the TMA unit pays a fixed cost per
     // box, and twelve small boxes per stage made the wgrad load-bound.
@@ -224,28 +221,24 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       const uint32_t b_tx = (MODE == 2) ? (uint32_t)n_bbox * box_tx : (uint32_t)(block_n * 128);
-      const int tl = (tile - blockIdx.x) / gridDim.x;
-      if (p.trace && blockIdx.x == 0 && tl < 64) p.trace[(0 * 64 + tl) * 4 + 0] = clock64();
       for (int it = 0; it < t.n_iters; ++it) {
         mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t* a_dst = smem + s * stage_bytes;
-        uint8_t* b_dst = a_dst + a_bytes;
-        const bool skip_a = (p.dbg & 1) && it >= stages, skip_b = (p.dbg & 2) && it >= stages;  // timing experiments
-        const uint32_t tx = (skip_a ? 0u : a_tx) + (skip_b ? 0u : b_tx);
-        if (tx) mbar_expect_tx(&full[s], tx);
-        else mbar_arrive(&full[s]);
-        if (MODE == 0) {
-          if (!skip_a) tma_load_4d(a_dst, &tmA, &full[s], cc * KC, t.x0 + sx - p.pad, t.y0 + r - p.pad, t.b);
-          if (!skip_b) tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0);
-        } else {
-          if (!skip_a) tma_load_5d(a_dst, &tmA, &full[s], 0, px0, py0, bb, t.m0 / KC);
-          if (!skip_b) {
+        if (elect_one()) {
+          uint8_t* a_dst = smem + s * stage_bytes;
+          uint8_t* b_dst = a_dst + a_bytes;
+          mbar_expect_tx(&full[s], a_tx + b_tx);
+          if (MODE == 0) {
+            tma_load_4d(a_dst, &tmA, &full[s], cc * KC, t.x0 + sx - p.pad, t.y0 + r - p.pad, t.b);
+            tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0);
+          } else {
+            tma_load_5d(a_dst, &tmA, &full[s], 0, px0, py0, bb, t.m0 / KC);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               if (j < n_bbox)
                 tma_load_5d(b_dst + j * box_tx, &tmB, &full[s], 0, px0 + g_dx[j], py0 + g_dy[j], bb, g_cg[j]);
           }
         }
+        __syncwarp();
         if (++s == stages) s = 0, ph ^= 1u;
         if (MODE == 2) {
           px0 += p.TW;
@@ -261,8 +254,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // =========================== MMA issuer ===========================
+    // whole warp in the loop, one elected lane issues: back-to-back UTCHMMA without the ELECT/BRA.U.ANY loops (see elect_one)
     const uint32_t idesc = umma_idesc(TF32 ? 2 : 1, A_MN ? 1 : 0, B_MN ? 1 : 0, 128, block_n);
     int s = 0;
     uint32_t ph = 0;
@@ -271,52 +265,51 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const TileCoord t = decode_tile<MODE>(p, tile);
       if (t.n_iters == 0) continue;
       const uint32_t buf = p.nbuf == 2 ? (local & 1u) : 0u, aph = p.nbuf == 2 ? ((local >> 1) & 1u) : (local & 1u);
-      const int tl = (int)local;
       ++local;
-      if (p.trace && blockIdx.x == 0 && tl < 64) p.trace[(1 * 64 + tl) * 4 + 0] = clock64();
       mbar_wait(&acce[buf], aph ^ 1u);  // the epilogue has drained this accumulator buffer
       tc_fence_after();
-      if (p.trace && blockIdx.x == 0 && tl < 64) p.trace[(1 * 64 + tl) * 4 + 1] = clock64();
       const uint32_t dacc = tmem + buf * (uint32_t)p.tmem_cols;
       for (int it = 0; it < t.n_iters; ++it) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
-        // K-major: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzled row.
-        // MN-major: 128 B-wide column groups LBO = rows_a*128 B apart (as the 5-D TMA box lays them down), K advances UK
-        // rows of 128 B per MMA; the K rows come in groups SBO apart: 8 rows / 1024 B for 16-bit operands (SWIZZLE_128B),
-        // 4 rows / 512 B for tf32 (SWIZZLE_128B_BASE32B, the only MN-major layout tcgen05 takes for 32-bit operands).
-        constexpr uint32_t MN_LAYOUT = TF32 ? 1u : 2u, MN_SBO = TF32 ? 512u : 1024u;
-        const uint32_t lbo = (uint32_t)rows_a * 128u;
-        const int ksteps = (MODE == 2) ? p.ksteps : 4;
-        if (MODE == 2 && mp == 2) {
-          // two 128-row sub-tiles share the B stage.  (A separate loop, not a predicated second MMA inside the common
-          // loop: a predicated-off UTCHMMA still cost the single-tile path 25 %.)
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = umma_desc(a_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT);
-            const uint64_t adesc2 = umma_desc(a_addr + (128 / KC) * lbo + k * UK * 128, lbo, MN_SBO, MN_LAYOUT);
-            const uint64_t bdesc = umma_desc(b_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT);
-            tc_mma<TF32>(dacc, adesc, bdesc, idesc, (uint32_t)((it | k) != 0));
-            tc_mma<TF32>(dacc + (uint32_t)p.acc_cols, adesc2, bdesc, idesc, (uint32_t)((it | k) != 0));
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint32_t b_addr = a_addr + a_bytes;
+          // K-major: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzled row.
+          // MN-major: 128 B-wide column groups LBO = rows_a*128 B apart (as the 5-D TMA box lays them down), K advances UK
+          // rows of 128 B per MMA; the K rows come in groups SBO apart: 8 rows / 1024 B for 16-bit operands (SWIZZLE_128B),
+          // 4 rows / 512 B for tf32 (SWIZZLE_128B_BASE32B, the only MN-major layout tcgen05 takes for 32-bit operands).
+          constexpr uint32_t MN_LAYOUT = TF32 ? 1u : 2u, MN_SBO = TF32 ? 512u : 1024u;
+          const uint32_t lbo = (uint32_t)rows_a * 128u;
+          const int ksteps = (MODE == 2) ? p.ksteps : 4;
+          if (MODE == 2 && mp == 2) {
+            // two 128-row sub-tiles share the B stage
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = umma_desc(a_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT);
+              const uint64_t adesc2 = umma_desc(a_addr + (128 / KC) * lbo + k * UK * 128, lbo, MN_SBO, MN_LAYOUT);
+              const uint64_t bdesc = umma_desc(b_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT);
+              tc_mma<TF32>(dacc, adesc, bdesc, idesc, (uint32_t)((it | k) != 0));
+              tc_mma<TF32>(dacc + (uint32_t)p.acc_cols, adesc2, bdesc, idesc, (uint32_t)((it | k) != 0));
+            }
+          } else {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = A_MN ? umma_desc(a_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
+                                          : umma_desc_sw128(a_addr + k * 32, 16, 1024);
+              const uint64_t bdesc = B_MN ? umma_desc(b_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
+                                          : umma_desc_sw128(b_addr + k * 32, 16, 1024);
+              // narrow tiles rotate their K steps over 2-4 accumulators that the epilogue adds (consecutive MMAs into
+              // ONE accumulator serialise on its read-modify-write)
+              const int a = k & (p.nacc - 1);
+              tc_mma<TF32>(dacc + (uint32_t)(a * p.acc_cols), adesc, bdesc, idesc, (uint32_t)(it != 0 || k >= p.nacc));
+            }
           }
-        } else {
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = A_MN ? umma_desc(a_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
-                                        : umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? umma_desc(b_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
-                                        : umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            // consecutive MMAs into ONE accumulator serialise on its ~140-cycle read-modify-write latency (measured: 560
-            // cycles per 4-MMA stage whatever N is); narrow tiles therefore rotate over 2-4 accumulators that the epilogue adds
-            const int a = k & (p.nacc - 1);
-            tc_mma<TF32>(dacc + (uint32_t)(a * p.acc_cols), adesc, bdesc, idesc, (uint32_t)(it != 0 || k >= p.nacc));
-          }
+          tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
         }
-        tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+        __syncwarp();
         if (++s == stages) s = 0, ph ^= 1u;
       }
-      tc_commit(&accf[buf]);  // accumulator complete
-      if (p.trace && blockIdx.x == 0 && tl < 64) p.trace[(1 * 64 + tl) * 4 + 2] = clock64();
+      if (elect_one()) tc_commit(&accf[buf]);  // accumulator complete
+      __syncwarp();
     }
   } else if (warp >= 2) {
     // =========================== epilogue ===========================
@@ -326,18 +319,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int CWMAX = OUT_F32_ONLY ? 32 : 64;
     const int q4 = warp & 3;           // TMEM lane quarter this warp may read
     const int row = q4 * 32 + lane;
-    const bool issuer = (threadIdx.x == 64);
+    const bool issuer = elect_one() && warp == 2;  // one fixed lane of warp 2 owns the bulk-store groups
     uint32_t local = 0, chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<MODE>(p, tile);
       if (t.n_iters == 0) continue;
       const uint32_t buf = p.nbuf == 2 ? (local & 1u) : 0u, aph = p.nbuf == 2 ? ((local >> 1) & 1u) : (local & 1u);
-      const int tl = (int)local;
       ++local;
-      if (p.trace && blockIdx.x == 0 && tl < 64 && issuer) p.trace[(2 * 64 + tl) * 4 + 0] = clock64();
       mbar_wait(&accf[buf], aph);
       tc_fence_after();
-      if (p.trace && blockIdx.x == 0 && tl < 64 && issuer) p.trace[(2 * 64 + tl) * 4 + 1] = clock64();
       const uint32_t tbase = tmem + buf * (uint32_t)p.tmem_cols + ((uint32_t)(q4 * 32) << 16);
 
       bool ok = true;
@@ -388,7 +378,6 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        if (p.trace && blockIdx.x == 0 && tl < 64 && issuer && c == 0) p.trace[(0 * 64 + tl) * 4 + 1] = clock64();  // after tmem ld
         if (last) {  // every TMEM read of this tile is done: hand the accumulator buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -453,10 +442,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ---- registers -> swizzled staging row -> TMA store ----
         uint8_t* sbuf = staging + (chunk_ctr & 1u) * STAGING_BYTES;
         ++chunk_ctr;
-        if (p.trace && blockIdx.x == 0 && tl < 64 && issuer && c == 0) p.trace[(0 * 64 + tl) * 4 + 2] = clock64();  // after math
         if (issuer) bulk_wait_read<1>();  // the store issued from this buffer two chunks ago has read it
         named_bar_sync(1, 128);
-        if (p.trace && blockIdx.x == 0 && tl < 64 && issuer && c == 0) p.trace[(0 * 64 + tl) * 4 + 3] = clock64();  // after wait+bar
         uint4 q[8];
         if (f32_out) {
           if (TF32 && MODE != 2 && !p.out_fp32) {
@@ -492,8 +479,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < 8; ++j) srow[j ^ (row & 7)] = q[j];
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
-        if (p.trace && blockIdx.x == 0 && tl < 64 && issuer && c == 0) p.trace[(1 * 64 + tl) * 4 + 3] = clock64();  // after sts+fence+bar
-        if (issuer && !(p.dbg & 4)) {
+        if (issuer) {
           if (MODE == 2) tma_reduce_add_2d(&tmO, sbuf, nb, t.m0 + h * 128);
           else tma_store_4d(&tmO, sbuf, nb, t.x0, t.y0, t.b);
           bulk_commit();
@@ -521,7 +507,6 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (half * 32 < CW && col < p.N) atomicAdd(p.col_sum + col, v[0]);
           }
         }
-        if (p.trace && blockIdx.x == 0 && tl < 64 && issuer && c < 2) p.trace[(2 * 64 + tl) * 4 + 2 + c] = clock64();
       }
     }
     if (issuer) bulk_wait<0>();  // all stores have landed before the CTA (and its shared memory) goes away
@@ -636,20 +621,6 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
   p.tmem_cols = p.acc_cols * p.nacc * p.mpair;  // per accumulator buffer
   p.nbuf = 2 * p.tmem_cols <= 512 ? 2 : 1;
   p.total_tiles = (int)tiles;
-  {
-    const char* e = getenv("SZN_TRACE");
-    p.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr;
-  }
-  {
-    static int dbg = -1, dbg_mode = 0;
-    if (dbg < 0) {
-      const char* e = getenv("SZN_DBG");
-      dbg = e ? atoi(e) : 0;
-      e = getenv("SZN_DBG_MODE");
-      dbg_mode = e ? atoi(e) : 0;
-    }
-    p.dbg = MODE == dbg_mode ? dbg : 0;
-  }
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool attr_set = false;
   if (!attr_set) {
