@@ -9,7 +9,12 @@
  *   - the caller owns every buffer (device pointers unless stated), nothing is allocated here,
  *     nothing synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*).
  *   - dtype: SZN_F32 = fp32 storage, TF32 tensor-core products, fp32 accumulate;
- *            SZN_BF16 = bf16 storage, bf16 products, fp32 accumulate.
+ *            SZN_BF16 = bf16 storage, bf16 products, fp32 accumulate;
+ *            SZN_F32X3 = fp32-grade: every value v is stored as two bf16 planes hi = bf16(v), lo = bf16(v - hi)
+ *            (a pixel row of C channels is [hi_0..hi_{C-1} | lo_0..lo_{C-1}], the same 4C bytes as fp32; packed
+ *            weights are two planes, hi then lo) and every product is the error-compensated sum
+ *            hi*hi + lo*hi + hi*lo of three kind::f16 MMAs with fp32 accumulate (relative error ~2^-16 per product
+ *            against 2^-11 for TF32): the precision the reference's fp32 CPU path is held to (models.py:114-160).
  *   - trunk activations are NHWC ([B][H][W][C], channels contiguous); weights for the tensor-core
  *     kernels are [Cout][R*S][Cin] ("OHWI") in the activation dtype; the public tensors of the
  *     reference API (input image, returned score) stay NCHW fp32.
@@ -23,6 +28,7 @@ extern "C" {
 
 #define SZN_F32 0
 #define SZN_BF16 1
+#define SZN_F32X3 2
 
 #define SZN_ERR_ARG (-1)
 #define SZN_ERR_CUDA (-2)
@@ -82,7 +88,8 @@ int szn_pack_weight_dgrad(int dtype, const float* w_oihw, void* out, int O, int 
  * weights) is folded back to dx[B,H,W,C] by summing the <= R*S window positions that cover each pixel */
 int szn_col2im(int dtype, const void* dcol, void* dx, int B, int H, int W, int C, int R, int S, void* stream);
 int szn_unpack_wgrad(const float* dw_ohwi, float* g_oihw, int O, int I, int R, int S, void* stream);
-int szn_cast(int dtype, const float* in, void* out, long long n, void* stream);
+/* fp32 [rows][C] -> the storage format `dtype` (row length C matters for SZN_F32X3's plane layout) */
+int szn_cast(int dtype, const float* in, void* out, long long rows, int C, void* stream);
 
 /* Dropout2d(p=0.5) (models.py:86,91): scale[n] in {0,2}, one value per (image, channel) */
 int szn_dropout_scale(float* scale, int n, unsigned long long seed, void* stream);

@@ -195,55 +195,125 @@ def test_cosine_loss_properties_full_size(head):
     assert abs(got_mse - ref_mse) < 1e-5 * max(1.0, abs(ref_mse))
 
 
-def test_model_full_size_forward_vs_oracle_and_batch_consistency():
-    """Full-size forward of one image against the CPU oracle (the reference's fp32 semantics), run alone (B=1) and as
-    image 3 of the B=8 batch; then one whole training step at B=8."""
+_ORACLE_CACHE = {}
+
+
+def _oracle_full_size(init):
+    """fp32 CPU oracle of image 3 of the seeded batch: forward (both heads), cosine loss, and its backward with the
+    dense `upscore` weight frozen (train.py:324-327 never optimises it; as written its gradient costs ~150 s more).
+    One pass per init (~600 GFLOP forward on the host cores), shared by the precision cases."""
+    if init in _ORACLE_CACHE:
+        return _ORACLE_CACHE[init]
     import zeroshotsemanticsegmentation_b200 as szn
     from zeroshotsemanticsegmentation_b200 import synth
-    U = szn.utils
-    m = synth.init_model_(szn.FCN32s(D), seed=1337).to(DEV).eval()
+    torch.manual_seed(1337)
+    m = szn.FCN32s(D)  # torch's default conv init under the reference's seed (train.py:62-64), models.py:104-108
+    if init == "he":
+        synth.init_model_(m, seed=1337)  # the bench's He-style init (activations stay O(1) through the 15 ReLU layers)
+    params = {k: v.detach().clone().contiguous() for k, v in m.state_dict().items()}
     x, lab, table = synth.synth_batch(B, H, W, C, D, seed=1337)
-    with torch.no_grad():
-        params = {k: v.detach().cpu().contiguous() for k, v in m.state_dict().items()}
-        f_ref, s_ref = O.forward(x[3:4], params, "both")  # ~600 GFLOP on the host cores (dense upscore as written)
-    x, table = x.to(DEV), table.to(DEV)
+    pr = {k: v.clone().requires_grad_("upscore" not in k and not k.startswith("seenmask")) for k, v in params.items()}
+    f_ref, s_ref = O.forward(x[3:4], pr, "both")
+    loss = O.cosine_loss(f_ref, lab[3:4], O.target_embed_from_labels(lab[3:4], table))
+    loss.backward()
+    grads = {k: v.grad.clone() for k, v in pr.items() if v.grad is not None}
+    out = dict(params=params, x=x, lab=lab, table=table, f=f_ref.detach(), s=s_ref.detach(), loss=float(loss.detach()),
+               grads=grads)
+    _ORACLE_CACHE[init] = out
+    return out
+
+
+def _rel(a, b):
+    return float((a.detach().cpu().float() - b).abs().max() / b.abs().max())
+
+
+def _l2(a, b):
+    return float((a.detach().cpu().double() - b.double()).norm() / b.double().norm())
+
+
+@pytest.mark.parametrize("init", ["he", "default"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_model_full_size_forward_vs_oracle_and_batch_consistency(precision, init):
+    """Full-size forward of one image against the CPU oracle (the reference's fp32 semantics), run alone (B=1) and as
+    image 3 of the B=8 batch, under the reference's default init and under the bench's He-style init.
+
+    precision="fp32" (3 x bf16 error-compensated products, the parity mode) is held to the north star's 1e-3 STRICTLY, for
+    the embedding score f AND the 2-channel seen-mask score s, and its full-size gradients are compared with the oracle.
+    precision="tf32" (the throughput mode) is reported and held to what 16 layers of 2^-11 products can give."""
+    import zeroshotsemanticsegmentation_b200 as szn
+    U = szn.utils
+    ref = _oracle_full_size(init)
+    m = szn.FCN32s(D, precision=precision)
+    m.load_state_dict(ref["params"])
+    m = m.to(DEV).eval()
+    x, lab, table = ref["x"].to(DEV), ref["lab"].to(DEV), ref["table"].to(DEV)
+    f_ref, s_ref = ref["f"], ref["s"]
     with torch.no_grad():
         f8, s8 = m(x, mode="both")
         f1, s1 = m(x[3:4].contiguous(), mode="both")
     assert f8.shape == (B, D, H, W) and s8.shape == (B, 2, H, W) and torch.isfinite(f8).all()
-
-    def rel(a, b):
-        return float((a.cpu() - b).abs().max() / b.abs().max())
-
-    e = dict(f8=rel(f8[3:4], f_ref), f1=rel(f1, f_ref), s8=rel(s8[3:4], s_ref), s1=rel(s1, s_ref),
-             f8_vs_f1=rel(f8[3:4], f1.cpu()), s8_vs_s1=rel(s8[3:4], s1.cpu()))
-    print("full-size forward, max-abs-diff / max-abs-ref:", {k: "%.3e" % v for k, v in e.items()},
-          "bit-identical B=8 vs B=1:", torch.equal(f8[3:4], f1))
-    # north star: the score within 1e-3 (max-abs-diff / max-abs-ref) of the reference's fp32 forward.  Measured on B200
-    # with this seeded He-style init: 9.7e-4 -- 16 layers of TF32 products and TF32-rounded activations sit right at the
-    # bound at full size (the small golden cases measure 1.2-2.3e-4).  The kernels are deterministic, so is this number on
-    # a given part; the assertion leaves 20 % for another SM count (other tile shapes -> other summation order).
-    assert e["f8"] < 1.2e-3 and e["f1"] < 1.2e-3
-    # the 2-channel seen-mask score has the same absolute noise but its maximum is only ~2 sigma of its values (the
-    # 300-channel score's is ~5 sigma), so the same metric reads 2.3e-3
-    assert e["s8"] < 5e-3 and e["s1"] < 5e-3
-    # other batch sizes may pick other tile shapes, i.e. another fp32 summation order, and a last-bit difference can move
-    # a TF32 rounding of a stored activation: B=8 and B=1 agree like each agrees with the oracle, not bit for bit
-    assert e["f8_vs_f1"] < 2e-3 and e["s8_vs_s1"] < 5e-3
+    e = dict(f8=_rel(f8[3:4], f_ref), f1=_rel(f1, f_ref), s8=_rel(s8[3:4], s_ref), s1=_rel(s1, s_ref),
+             f8_vs_f1=_rel(f8[3:4], f1.cpu()), s8_vs_s1=_rel(s8[3:4], s1.cpu()))
+    print("full-size forward [%s, %s init], max-abs-diff / max-abs-ref:" % (precision, init),
+          {k: "%.3e" % v for k, v in e.items()}, "bit-identical B=8 vs B=1:", torch.equal(f8[3:4], f1))
+    if precision == "fp32":
+        # north star: "outputs match the reference forward within 1e-3 relative": strict, both heads, both inits
+        for k in ("f8", "f1", "s8", "s1", "f8_vs_f1", "s8_vs_s1"):
+            assert e[k] < 1e-3, (k, e[k])
+    else:
+        # TF32 (throughput mode): 16 layers of TF32 products and TF32-rounded activations sit AT the bound at full size
+        # with the He-style init (measured 9.7e-4; the 2-channel seen-mask score, whose maximum is only ~2 sigma of its
+        # values, reads 2.3e-3).  These numbers are carried in bench.py's JSON line; the strict gate is the fp32 case.
+        assert e["f8"] < 1.2e-3 and e["f1"] < 1.2e-3
+        assert e["s8"] < 5e-3 and e["s1"] < 5e-3
+        assert e["f8_vs_f1"] < 2e-3 and e["s8_vs_s1"] < 5e-3
     l_ref = O.infer_lbl(f_ref, table.cpu())
     l8 = U.infer_lbl_device(f8, table)[3].cpu().numpy()
     l1 = U.infer_lbl_device(f1, table)[0].cpu().numpy()
     agree8, agree1 = float((l8 == l_ref[0]).mean()), float((l1 == l_ref[0]).mean())
     print("end-to-end label agreement with the oracle: B=8 %.5f  B=1 %.5f" % (agree8, agree1))
-    assert agree8 > 0.99 and agree1 > 0.99  # measured 0.9997
-    # whole training step at full size: finite loss and gradients, frozen upscore untouched
-    m.train()
-    f = m(x, mode="fcn")
-    loss = U.cosine_loss(f, lab.to(DEV), table=table)
+    assert agree8 > (0.9995 if precision == "fp32" else 0.99) and agree1 > (0.9995 if precision == "fp32" else 0.99)
+
+    # ---- full-size gradients of the same image against the oracle (eval mode: no dropout on either side) ----
+    m.zero_grad(set_to_none=True)
+    f = m(x[3:4].contiguous(), mode="fcn")
+    loss = U.cosine_loss(f, lab[3:4], table=table)
     loss.backward()
-    assert np.isfinite(loss.item())
-    for n, p in m.named_parameters():
-        if "upscore" in n or n.startswith("seenmask"):
-            assert p.grad is None, n
-        else:
-            assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0, n
+    assert abs(loss.item() - ref["loss"]) < (1e-5 if precision == "fp32" else 1e-3)
+    ge, gl = {}, {}
+    for n in ("score_fr.weight", "score_fr.bias", "fc7.weight", "fc7.bias", "fc6.bias", "conv5_3.weight", "conv3_1.weight",
+              "conv1_2.weight", "conv1_1.weight", "conv1_1.bias"):
+        g = dict(m.named_parameters())[n].grad
+        ge[n], gl[n] = _rel(g, ref["grads"][n]), _l2(g, ref["grads"][n])
+    print("full-size gradients [%s, %s init], max-abs-diff / max-abs-ref:" % (precision, init),
+          {k: "%.2e" % v for k, v in ge.items()})
+    print("full-size gradients [%s, %s init], relative L2 error:" % (precision, init), {k: "%.2e" % v for k, v in gl.items()})
+    if precision == "fp32":
+        # SURVEY 8d: "gradient of score_fr.weight and conv1_1.weight <= 1e-2 rel".  No gate lies between score_fr and the
+        # loss: tight in every norm.  Below the first ReLU a gradient is a sum over gate / pool-winner decisions, and the
+        # handful of pre-activations within ~1e-4 of zero decide differently on the two sides (two fp32 libraries do the
+        # same to each other): each such flip moves ONE term by O(1), which the max-norm sees and the L2 norm averages.
+        # Measured at 512x512 (B200): rel-L2 4e-5 (score_fr), 2e-3 (fc7), 6e-3 (conv5_3), 1.3e-2 (conv1_2), 1.5e-2
+        # (conv1_1) -- ten times tighter than the TF32 mode at every depth (conv1_1: 1.4e-1); at the reference's golden
+        # sizes conv1_1.weight is within 6e-3 (tests/test_model_gpu.py), inside SURVEY's 1e-2.
+        assert ge["score_fr.weight"] < 1e-3 and ge["score_fr.bias"] < 1e-3
+        for n in gl:
+            deep = n.startswith(("conv1", "conv2", "conv3"))
+            assert gl[n] < (3e-2 if deep else 1e-2), (n, gl[n])
+            assert ge[n] < (1e-1 if deep else 5e-2), (n, ge[n])
+    else:
+        assert ge["score_fr.weight"] < 1e-2 and ge["score_fr.bias"] < 1e-2 and gl["fc7.bias"] < 5e-2
+
+    if precision == "tf32" and init == "he":
+        # whole training step at full size: finite loss and gradients, frozen upscore untouched
+        m.train()
+        m.zero_grad(set_to_none=True)
+        f = m(x, mode="fcn")
+        loss = U.cosine_loss(f, lab, table=table)
+        loss.backward()
+        assert np.isfinite(loss.item())
+        for n, p in m.named_parameters():
+            if "upscore" in n or n.startswith("seenmask"):
+                assert p.grad is None, n
+            else:
+                assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0, n

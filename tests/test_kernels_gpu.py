@@ -21,28 +21,63 @@ def lib():
     return _lib
 
 
+PRECS = ["tf32", "bf16", "fp32"]  # "fp32" = the split (hi, lo) bf16-plane format, 3 x bf16 products
+
+
 def round_to(t, prec):
+    """Round to what the storage format represents exactly."""
     if prec == "bf16":
         return t.bfloat16().float()
+    if prec == "fp32":
+        hi = t.bfloat16().float()
+        return hi + (t - hi).bfloat16().float()
     i = t.contiguous().view(torch.int32)
     i = ((i + 0xFFF + ((i >> 13) & 1)) >> 13) << 13
     return i.view(torch.float32)
 
 
 def tdtype(prec):
-    return torch.bfloat16 if prec == "bf16" else torch.float32
+    return torch.float32 if prec == "tf32" else torch.bfloat16
 
 
 def dcode(prec):
-    return 1 if prec == "bf16" else 0
+    return {"tf32": 0, "bf16": 1, "fp32": 2}[prec]
+
+
+def planes(prec):
+    return 2 if prec == "fp32" else 1
+
+
+def to_store(t, prec):
+    """fp32 [..., C] -> device tensor in the storage format ([..., 2C] bf16 = hi | lo for the split format)."""
+    if prec == "fp32":
+        hi = t.bfloat16()
+        lo = (t - hi.float()).bfloat16()
+        return torch.cat([hi, lo], -1).contiguous().to(DEV)
+    return t.contiguous().to(DEV).to(tdtype(prec))
+
+
+def from_store(t, prec):
+    t = t.float().cpu()
+    if prec == "fp32":
+        C = t.shape[-1] // 2
+        return t[..., :C] + t[..., C:]
+    return t
+
+
+def act_buf(prec, *shape, fill=float("nan")):
+    """Uninitialised (NaN-filled) activation buffer [..., C] in the storage format."""
+    shape = list(shape)
+    shape[-1] *= planes(prec)
+    return torch.full(shape, fill, device=DEV, dtype=tdtype(prec))
 
 
 def nhwc(t, prec):  # NCHW fp32 cpu -> NHWC device tensor of the storage type
-    return t.permute(0, 2, 3, 1).contiguous().to(DEV).to(tdtype(prec))
+    return to_store(t.permute(0, 2, 3, 1), prec)
 
 
-def from_nhwc(t):
-    return t.float().cpu().permute(0, 3, 1, 2).contiguous()
+def from_nhwc(t, prec="tf32"):
+    return from_store(t, prec).permute(0, 3, 1, 2).contiguous()
 
 
 def ohwi(w, prec, o_pad=None):
@@ -50,7 +85,13 @@ def ohwi(w, prec, o_pad=None):
     out = w.permute(0, 2, 3, 1).reshape(O_, R * S, I)
     if o_pad and o_pad > O_:
         out = torch.cat([out, torch.zeros(o_pad - O_, R * S, I)], 0)
+    if prec == "fp32":  # two planes, hi then lo
+        hi = out.bfloat16()
+        return torch.cat([hi, (out - hi.float()).bfloat16()], 0).contiguous().to(DEV)
     return out.contiguous().to(DEV).to(tdtype(prec))
+
+
+TOL_STORE = {"tf32": 1e-3, "bf16": 1e-2, "fp32": 4e-5}  # outputs rounded to the storage type
 
 
 def relerr(a, b):
@@ -91,7 +132,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_fwd(prec, case):
     B, H, W, Cin, Cout, k, pad = case
@@ -102,19 +143,19 @@ def test_conv_fwd(prec, case):
     scale = (torch.rand(B, Cout, generator=g) < 0.5).float() * 2
     ref = F.relu(F.conv2d(x, w, b, padding=pad)) * scale[:, :, None, None]
     Ho, Wo = ref.shape[2:]
-    y = torch.full((B, Ho, Wo, Cout), float("nan"), device=DEV, dtype=tdtype(prec))
+    y = act_buf(prec, B, Ho, Wo, Cout)
     L = lib()
     L.call("szn_conv_fwd", dcode(prec), dp(nhwc(x, prec)), dp(ohwi(w, prec)), dp(b.to(DEV)),
            dp(y), B, H, W, Cin, Cout, k, k, pad, 1, dp(scale.to(DEV)), Cout, 0, Cout, st())
     torch.cuda.synchronize()
-    got = from_nhwc(y)
-    tol = 1e-3 if prec == "tf32" else 1e-2  # the kernel rounds its output to the storage type
+    got = from_nhwc(y, prec)
+    tol = TOL_STORE[prec]  # the kernel rounds its output to the storage type
     e = relerr(got, ref)
     print("conv_fwd", prec, case, "relerr", e)
     assert e < tol
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 def test_conv_fwd_fp32_out_no_relu(prec):
     B, H, W, Cin, Cout = 2, 5, 7, 128, 64
     g = torch.Generator().manual_seed(2)
@@ -135,12 +176,12 @@ def test_conv_fwd_fp32_out_no_relu(prec):
 def pack_dgrad(w, prec, mode=0):
     """Transposed data-gradient weights through the library's own pack kernel (what engine.py does)."""
     O_, I, R, S = w.shape
-    out = torch.empty((I, R * S, O_), device=DEV, dtype=tdtype(prec))
+    out = torch.empty((planes(prec) * I, R * S, O_), device=DEV, dtype=tdtype(prec))
     lib().call("szn_pack_weight_dgrad", dcode(prec), dp(w.contiguous().to(DEV)), dp(out), O_, I, R, S, O_, mode, st())
     return out
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_dgrad(prec, case):
     B, H, W, Cin, Cout, k, pad = case
@@ -153,22 +194,22 @@ def test_conv_dgrad(prec, case):
     scale = (torch.rand(B, Cin, generator=g) < 0.5).float() * 2
     (dx,) = torch.autograd.grad(y, x, dy)
     ref = dx * scale[:, :, None, None] * (ref_act > 0)
-    out = torch.full((B, H, W, Cin), float("nan"), device=DEV, dtype=tdtype(prec))
+    out = act_buf(prec, B, H, W, Cin)
     colsum = torch.zeros(Cin, device=DEV)
     L = lib()
     L.call("szn_conv_dgrad", dcode(prec), dp(nhwc(dy, prec)), dp(pack_dgrad(w, prec)), dp(out), B, H, W,
            Cin, Cout, k, k, pad, dp(nhwc(ref_act, prec)), dp(scale.to(DEV)), Cin, Cout, dp(colsum), st())
     torch.cuda.synchronize()
-    got = from_nhwc(out)
+    got = from_nhwc(out, prec)
     e = relerr(got, ref)
     print("conv_dgrad", prec, case, "relerr", e)
-    assert e < (1e-3 if prec == "tf32" else 1e-2)
+    assert e < TOL_STORE[prec]
     # fused bias gradient of the producer layer: column sums of exactly the values that were stored
     want = got.sum(dim=(0, 2, 3))
     assert relerr(colsum.cpu(), want) < 1e-5
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 def test_conv_dgrad_col2im(prec):
     """fc6-style data gradient: one GEMM against the (tap, ci)-major transposed weights + szn_col2im."""
     B, H, W, Cin, Cout, k = 2, 11, 12, 64, 128, 7
@@ -180,18 +221,18 @@ def test_conv_dgrad_col2im(prec):
     (ref,) = torch.autograd.grad(y, x, dy)
     Ho, Wo = y.shape[2:]
     L = lib()
-    dcol = torch.full((B, Ho, Wo, k * k * Cin), float("nan"), device=DEV, dtype=tdtype(prec))
+    dcol = act_buf(prec, B, Ho, Wo, k * k * Cin)
     L.call("szn_conv_dgrad", dcode(prec), dp(nhwc(dy, prec)), dp(pack_dgrad(w, prec, 1)), dp(dcol), B, Ho, Wo,
            k * k * Cin, Cout, 1, 1, 0, None, None, 0, Cout, None, st())
-    out = torch.full((B, H, W, Cin), float("nan"), device=DEV, dtype=tdtype(prec))
+    out = act_buf(prec, B, H, W, Cin)
     L.call("szn_col2im", dcode(prec), dp(dcol), dp(out), B, H, W, Cin, k, k, st())
     torch.cuda.synchronize()
-    e = relerr(from_nhwc(out), ref)
+    e = relerr(from_nhwc(out, prec), ref)
     print("conv_dgrad_col2im", prec, "relerr", e)
-    assert e < (1e-3 if prec == "tf32" else 2e-2)
+    assert e < {"tf32": 1e-3, "bf16": 2e-2, "fp32": 1e-4}[prec]
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_wgrad(prec, case):
     B, H, W, Cin, Cout, k, pad = case
@@ -212,7 +253,7 @@ def test_conv_wgrad(prec, case):
     assert e < 1e-4
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 def test_conv1_1(prec):
     B, H, W = 2, 13, 21
     g = torch.Generator().manual_seed(5)
@@ -221,12 +262,12 @@ def test_conv1_1(prec):
     b = torch.randn(64, generator=g)
     y = F.relu(F.conv2d(x, w, b, padding=100))
     Ho, Wo = y.shape[2:]
-    out = torch.empty((B, Ho, Wo, 64), device=DEV, dtype=tdtype(prec))
+    out = act_buf(prec, B, Ho, Wo, 64)
     L = lib()
     L.call("szn_conv1_1_fwd", dcode(prec), dp(x.to(DEV)), dp(w.detach().to(DEV)), dp(b.to(DEV)),
            dp(out), B, H, W, 100, st())
     torch.cuda.synchronize()
-    assert relerr(from_nhwc(out), y.detach()) < (1e-3 if prec == "tf32" else 1e-2)
+    assert relerr(from_nhwc(out, prec), y.detach()) < TOL_STORE[prec]
     dy = round_to(torch.randn(y.shape, generator=g), prec)
     pre = F.conv2d(x, w, padding=100)
     (dw,) = torch.autograd.grad(pre, w, dy)
@@ -237,7 +278,7 @@ def test_conv1_1(prec):
     assert relerr(gw.cpu(), dw) < 1e-4
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("hw", [(7, 9), (8, 8), (45, 23)])
 def test_pool(prec, hw):
     B, C = 2, 64
@@ -248,39 +289,42 @@ def test_pool(prec, hw):
     y[:, :, 0:2, 0:2] = y[:, :, 0:1, 0:1]  # exact non-zero ties: the first position must win
     y.requires_grad_(True)
     p = F.max_pool2d(y, 2, stride=2, ceil_mode=True)
-    out = torch.empty((B, p.shape[2], p.shape[3], C), device=DEV, dtype=tdtype(prec))
+    out = act_buf(prec, B, p.shape[2], p.shape[3], C)
     L = lib()
     yd = nhwc(y.detach(), prec)
     L.call("szn_pool_fwd", dcode(prec), dp(yd), dp(out), B, H, W, C, st())
     torch.cuda.synchronize()
-    assert torch.equal(from_nhwc(out), p.detach())
+    assert torch.equal(from_nhwc(out, prec), p.detach())
     dpool = round_to(torch.randn(p.shape, generator=g), prec)
     (dy,) = torch.autograd.grad(p, y, dpool)
     ref = dy * (y.detach() > 0)
-    dyo = torch.empty((B, H, W, C), device=DEV, dtype=tdtype(prec))
+    dyo = act_buf(prec, B, H, W, C)
     csum = torch.zeros(C, device=DEV)
     L.call("szn_pool_bwd", dcode(prec), dp(yd), dp(nhwc(dpool, prec)), dp(dyo), B, H, W, C, 1, dp(csum), st())
     torch.cuda.synchronize()
-    assert torch.equal(from_nhwc(dyo), ref)
+    assert torch.equal(from_nhwc(dyo, prec), ref)
     assert relerr(csum.cpu(), ref.sum(dim=(0, 2, 3))) < 1e-5  # fused bias gradient of the conv in front of the pool
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 def test_bias_grad_pack_unpack(prec):
     g = torch.Generator().manual_seed(7)
     rows, C, ld = 1000, 320, 320
     dy = round_to(torch.randn(rows, ld, generator=g), prec)
     db = torch.zeros(C, device=DEV)
     L = lib()
-    L.call("szn_bias_grad", dcode(prec), dp(dy.to(DEV).to(tdtype(prec))), dp(db), rows, C, ld, st())
+    L.call("szn_bias_grad", dcode(prec), dp(to_store(dy, prec)), dp(db), rows, C, ld, st())
     torch.cuda.synchronize()
     assert relerr(db.cpu(), dy.sum(0)) < 1e-5
     w = torch.randn(5, 64, 3, 3, generator=g)
-    out = torch.empty((8, 9, 64), device=DEV, dtype=tdtype(prec))
+    out = torch.empty((planes(prec) * 8, 9, 64), device=DEV, dtype=tdtype(prec))
     L.call("szn_pack_weight", dcode(prec), dp(w.to(DEV)), dp(out), 5, 64, 3, 3, 8, st())
     torch.cuda.synchronize()
     ref = round_to(w, prec).permute(0, 2, 3, 1).reshape(5, 9, 64)
-    assert torch.equal(out.float().cpu()[:5], ref) and (out.float().cpu()[5:] == 0).all()
+    got = out.float().cpu()
+    if prec == "fp32":
+        got = got[:8] + got[8:]  # hi plane + lo plane
+    assert torch.equal(got[:5], ref) and (got[5:] == 0).all()
     dw = torch.randn(5, 9, 64, generator=g)
     gg = torch.empty((5, 64, 3, 3), device=DEV)
     L.call("szn_unpack_wgrad", dp(dw.to(DEV)), dp(gg), 5, 64, 3, 3, st())

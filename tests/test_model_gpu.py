@@ -97,6 +97,51 @@ def test_forward_backward_ce21_golden(golden):
     assert agree > 0.995
 
 
+def test_fp32_grade_mode_matches_reference_goldens_strictly(golden):
+    """precision="fp32" (3 x bf16 error-compensated tensor-core products on split hi/lo storage): forward AND every
+    golden gradient of the UNMODIFIED reference, including conv1_1.weight -- the gate SURVEY 8d asks for (<= 1e-2) and the
+    TF32 mode can only meet in direction -- because activations now agree to ~1e-6 and ReLU / max-pool decisions no longer
+    flip."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    g = golden("ce21_37x53")
+    m = build(21, int(g["seed"]), precision="fp32").eval()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    t = torch.from_numpy(g["target"]).long().to(DEV)
+    score = m(x, mode="fcn")
+    e = rel(score.detach().cpu().numpy(), g["score"])
+    print("forward rel err (fp32-grade)", e)
+    assert e < 2e-5
+    loss = U.cross_entropy2d(score, t)
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * float(g["loss"])
+    loss.backward()
+    named = dict(m.named_parameters())
+    for name in ("score_fr.weight", "score_fr.bias", "fc7.bias", "conv1_1.weight", "conv1_1.bias"):
+        e = rel(named[name].grad.cpu().numpy(), g[name.replace(".", "__") + "__grad"])
+        print(name, "grad rel err vs reference (fp32-grade)", e)
+        # SURVEY 8d's gate for conv1_1.weight is 1e-2 (a handful of ReLU gates next to zero still flip); the head is tight
+        assert e < (1e-2 if name.startswith("conv1_1") else 1e-3), name
+    e3 = rel(m.conv3_2.weight.grad[::16, ::16].cpu().numpy(), g["conv3_2__weight__grad_sub"])
+    e6 = rel(m.fc6.weight.grad[::256, ::64].cpu().numpy(), g["fc6__weight__grad_sub"])
+    print("conv3_2.weight", e3, "fc6.weight", e6)
+    assert e3 < 1e-2 and e6 < 1e-3
+    assert (score.detach().max(1)[1].cpu().numpy() == g["lbl"]).mean() > 0.9999
+    # both heads + cosine loss on the 2 x 64 x 96 golden case
+    g = golden("cos_voc20_2x64x96")
+    tab = torch.from_numpy(g["table"]).float()
+    m = build(tab.shape[1], int(g["seed"]), precision="fp32").eval()
+    f, s = m(torch.from_numpy(g["x"]).to(DEV), mode="both")
+    assert rel(f.detach().cpu().numpy(), g["score"]) < 2e-5
+    assert rel(s.detach().cpu().numpy(), g["seenmask_score"]) < 2e-5
+    loss = U.cosine_loss(f, torch.from_numpy(g["target"]).long().to(DEV), table=tab.to(DEV))
+    loss.backward()
+    assert rel(m.score_fr.weight.grad.cpu().numpy(), g["score_fr__weight__grad"]) < 1e-3
+    e1 = l2(m.conv1_1.weight.grad.cpu().numpy(), g["conv1_1__weight__grad"])
+    e5 = l2(m.conv5_3.weight.grad[::32, ::32].cpu().numpy(), g["conv5_3__weight__grad_sub"])
+    print("rel-L2 grad error vs reference: conv1_1.weight", e1, "conv5_3.weight", e5)
+    assert e1 < 1e-2 and e5 < 1e-2  # (max-norm: a single flipped ReLU gate moves one term by O(1))
+    assert (U.infer_lbl(f.detach(), tab.to(DEV)) == g["lbl"]).mean() > 0.9999
+
+
 def test_forward_256_golden(golden):
     """BASELINE configs[0]: 1x3x256x256, 21 classes, forward + CE loss."""
     from zeroshotsemanticsegmentation_b200 import utils as U

@@ -1,5 +1,5 @@
 """Per-layer timing of the tensor-core conv kernels (fwd / dgrad / wgrad) at the bench shapes, CUDA events, GPU box.
-usage: python tools/bench_layers.py [tf32|bf16] [B] [reps]"""
+usage: python tools/bench_layers.py [tf32|bf16|fp32] [B] [reps] [layer,layer,...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,7 +10,8 @@ prec = sys.argv[1] if len(sys.argv) > 1 else "tf32"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 only = sys.argv[4].split(",") if len(sys.argv) > 4 else None
-dt, td = (0, torch.float32) if prec == "tf32" else (1, torch.bfloat16)
+dt, td = {"tf32": (0, torch.float32), "bf16": (1, torch.bfloat16), "fp32": (2, torch.bfloat16)}[prec]
+npl = 2 if prec == "fp32" else 1  # split storage: [hi | lo] bf16 planes per pixel row / two weight planes
 dev = "cuda"
 st = torch.cuda.current_stream().cuda_stream
 layers = []
@@ -39,18 +40,18 @@ for name, H, W, cin, cout, k, pad in layers:
     if only and name not in only:
         continue
     Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
-    x = torch.randn(B, H, W, cin, device=dev).to(td)
-    y = torch.empty(B, Ho, Wo, cout, device=dev, dtype=td)
-    dy = torch.randn(B, Ho, Wo, cout, device=dev).to(td)
-    dx = torch.empty(B, H, W, cin, device=dev, dtype=td)
-    wt = (torch.randn(cout, k * k, cin, device=dev) * 0.01).to(td)
-    wd = (torch.randn(cin, k * k, cout, device=dev) * 0.01).to(td)
+    x = torch.randn(B, H, W, npl * cin, device=dev).to(td)
+    y = torch.empty(B, Ho, Wo, npl * cout, device=dev, dtype=td)
+    dy = torch.randn(B, Ho, Wo, npl * cout, device=dev).to(td)
+    dx = torch.empty(B, H, W, npl * cin, device=dev, dtype=td)
+    wt = (torch.randn(npl * cout, k * k, cin, device=dev) * 0.01).to(td)
+    wd = (torch.randn(npl * cin, k * k, cout, device=dev) * 0.01).to(td)
     bias = torch.zeros(cout, device=dev)
     dw = torch.zeros(cout, k * k * cin, device=dev)
     fl = 2.0 * B * Ho * Wo * cout * k * k * cin
     t_f = timeit(lambda: _lib.call("szn_conv_fwd", dt, x.data_ptr(), wt.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, W, cin, cout, k, k, pad, 1, None, 0, 0, cout, st))
     if name == "fc6":
-        dcol = torch.empty(B, Ho, Wo, k * k * cin, device=dev, dtype=td)
+        dcol = torch.empty(B, Ho, Wo, npl * k * k * cin, device=dev, dtype=td)
         def dg():
             _lib.call("szn_conv_dgrad", dt, dy.data_ptr(), wd.data_ptr(), dcol.data_ptr(), B, Ho, Wo, k * k * cin, cout, 1, 1, 0, None, None, 0, cout, None, st)
             _lib.call("szn_col2im", dt, dcol.data_ptr(), dx.data_ptr(), B, H, W, cin, k, k, st)

@@ -26,7 +26,7 @@ SIGNATURES = {
     "szn_pack_weight_dgrad": [I, P, P, I, I, I, I, I, I, P],
     "szn_col2im": [I, P, P, I, I, I, I, I, I, P],
     "szn_unpack_wgrad": [P, P, I, I, I, I, P],
-    "szn_cast": [I, P, P, LL, P],
+    "szn_cast": [I, P, P, LL, I, P],
     "szn_dropout_scale": [P, I, ULL, P],
     "szn_upsample32_crop_fwd": [P, P, I, I, I, I, I, I, I, I, P],
     "szn_upsample32_crop_bwd": [I, P, P, I, I, I, I, I, I, I, I, P],
@@ -47,7 +47,7 @@ SIGNATURES = {
     "szn_adam_step": [P, P, P, P, LL] + [ctypes.c_float] * 6 + [P],
 }
 
-F32, BF16 = 0, 1
+F32, BF16, F32X3 = 0, 1, 2
 
 _lib = None
 

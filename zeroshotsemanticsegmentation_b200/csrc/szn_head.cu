@@ -3,15 +3,9 @@
 // These stages are HBM-bound: one coalesced pass over the (B,D,H,W) score tensor each.
 #include "szn_internal.h"
 #include "szn_ptx.cuh"
+#include "szn_store.cuh"
 
 namespace szn {
-
-template <typename T>
-__device__ __forceinline__ T hfrom_float(float f);
-template <>
-__device__ __forceinline__ float hfrom_float<float>(float f) { return to_tf32(f); }
-template <>
-__device__ __forceinline__ __nv_bfloat16 hfrom_float<__nv_bfloat16>(float f) { return __float2bfloat16_rn(f); }
 
 constexpr int UPK = 64, UPS = 32, UPCROP = 19;
 
@@ -108,7 +102,7 @@ __global__ void __launch_bounds__(128) upsample_fwd_kernel(const float* __restri
 // NS column slots per thread (slot j = columns (threadIdx.x + j * blockDim.x) * VEC ...), so W <= blockDim.x * VEC * NS:
 // native-size PASCAL images (e.g. 500 x 375, train.py:82-84 feeds them unpadded at batch size 1) take VEC = 1, NS = 2.
 template <typename T, int VEC, int NS>
-__global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ g, T* __restrict__ ds, int B, int D,
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ g, void* __restrict__ ds, int B, int D,
                                                            int H, int W, int hs, int ws, int ld, int coff) {
   extern __shared__ float col[];  // [W]
   const int plane = blockIdx.x;
@@ -167,7 +161,7 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        if (sub == 0 && ix < ws) ds[(((long long)b * hs + iy) * ws + ix) * ld + coff + d] = hfrom_float<T>(acc);
+        if (sub == 0 && ix < ws) Store<T>::store_elem(ds, ((long long)b * hs + iy) * ws + ix, ld, coff + d, acc);
       }
       __syncthreads();
     }
@@ -218,7 +212,7 @@ __global__ void deconv_fwd_kernel(const float* __restrict__ s, const float* __re
 // ds[b,iy,ix,coff+ci] = sum_{j,ky,kx} g[b,j,32iy+ky-19,32ix+kx-19] wd[ci][j][ky][kx]   (one CTA per (b,iy,ix))
 template <typename T>
 __global__ void __launch_bounds__(256) deconv_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ wd,
-                                                           T* __restrict__ ds, int B, int Ci, int Co, int H, int W,
+                                                           void* __restrict__ ds, int B, int Ci, int Co, int H, int W,
                                                            int hs, int ws, int ld, int coff) {
   __shared__ float red[8];
   const int ix = blockIdx.x % ws, iy = (blockIdx.x / ws) % hs, b = blockIdx.x / (ws * hs);
@@ -239,7 +233,7 @@ __global__ void __launch_bounds__(256) deconv_dgrad_kernel(const float* __restri
     if (threadIdx.x == 0) {
       float t = 0.f;
       for (int k = 0; k < 8; ++k) t += red[k];
-      ds[(((long long)b * hs + iy) * ws + ix) * ld + coff + ci] = hfrom_float<T>(t);
+      Store<T>::store_elem(ds, ((long long)b * hs + iy) * ws + ix, ld, coff + ci, t);
     }
     __syncthreads();
   }
@@ -626,7 +620,7 @@ extern "C" int szn_upsample32_crop_fwd(const float* s, float* out, int B, int D,
 }
 
 template <typename T>
-static void launch_upsample_bwd(const float* g, T* ds, int B, int D, int H, int W, int hs, int ws, int ld, int coff,
+static void launch_upsample_bwd(const float* g, void* ds, int B, int D, int H, int W, int hs, int ws, int ld, int coff,
                                 bool v4, cudaStream_t st) {
   const unsigned grid = (unsigned)((long long)B * D);
   const size_t smem = (size_t)W * sizeof(float);
@@ -648,8 +642,9 @@ extern "C" int szn_upsample32_crop_bwd(int dtype, const float* g, void* ds, int 
   const bool v4 = W % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
   if (W > 1024) return set_error(SZN_ERR_UNSUPPORTED, "szn_upsample32_crop_bwd: W > 1024");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == SZN_BF16) launch_upsample_bwd<__nv_bfloat16>(g, (__nv_bfloat16*)ds, B, D, H, W, hs, ws, ld, coff, v4, st);
-  else launch_upsample_bwd<float>(g, (float*)ds, B, D, H, W, hs, ws, ld, coff, v4, st);
+  if (dtype == SZN_BF16) launch_upsample_bwd<__nv_bfloat16>(g, ds, B, D, H, W, hs, ws, ld, coff, v4, st);
+  else if (dtype == SZN_F32X3) launch_upsample_bwd<SplitBf16>(g, ds, B, D, H, W, hs, ws, ld, coff, v4, st);
+  else launch_upsample_bwd<float>(g, ds, B, D, H, W, hs, ws, ld, coff, v4, st);
   return check_launch("szn_upsample32_crop_bwd");
 }
 
@@ -664,9 +659,11 @@ extern "C" int szn_deconv_small_dgrad(int dtype, const float* g, const float* wd
                                       int W, int hs, int ws, int ld, int coff, void* stream) {
   const unsigned grid = (unsigned)(B * hs * ws);
   if (dtype == SZN_BF16)
-    deconv_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(g, wd, (__nv_bfloat16*)ds, B, Ci, Co, H, W, hs, ws, ld, coff);
+    deconv_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(g, wd, ds, B, Ci, Co, H, W, hs, ws, ld, coff);
+  else if (dtype == SZN_F32X3)
+    deconv_dgrad_kernel<SplitBf16><<<grid, 256, 0, (cudaStream_t)stream>>>(g, wd, ds, B, Ci, Co, H, W, hs, ws, ld, coff);
   else
-    deconv_dgrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(g, wd, (float*)ds, B, Ci, Co, H, W, hs, ws, ld, coff);
+    deconv_dgrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(g, wd, ds, B, Ci, Co, H, W, hs, ws, ld, coff);
   return check_launch("szn_deconv_small_dgrad");
 }
 

@@ -3,6 +3,7 @@
 // bias gradients, weight layout packing, Dropout2d channel masks (models.py:86,91).
 #include "szn_internal.h"
 #include "szn_ptx.cuh"
+#include "szn_store.cuh"
 
 namespace szn {
 
@@ -35,11 +36,16 @@ __device__ __forceinline__ float as_float<__nv_bfloat16>(__nv_bfloat16 v) { retu
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) conv1_1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*OIHW [64][3][3][3]*/,
-                                                          const float* __restrict__ bias, T* __restrict__ y, int B, int H,
+                                                          const float* __restrict__ bias, void* __restrict__ y, int B, int H,
                                                           int W, int Ho, int Wo, int pad) {
+  using S = Store<T>;
+  constexpr int VN = S::VN;                          // channels per vector
+  constexpr int ROWB = (int)S::row_bytes(64);        // bytes of one pixel row (64 channels)
+  constexpr int NCH = ROWB / 16;                     // 16-byte chunks per row: 16 (fp32, split) / 8 (bf16)
+  constexpr int NV = 64 / VN;                        // channel vectors per row
   __shared__ __align__(16) float sw_[27 * 64];  // [k][co]
   __shared__ float sb[64];
-  __shared__ __align__(16) T tile[128 * 64];
+  __shared__ __align__(16) uint4 tile[128 * NCH];
   for (int i = threadIdx.x; i < 27 * 64; i += 128) {
     const int co = i & 63, k = i >> 6;
     const int tap = k / 3, c = k - tap * 3;
@@ -67,30 +73,18 @@ __global__ void __launch_bounds__(128) conv1_1_fwd_kernel(const float* __restric
         for (int c = 0; c < 3; ++c)
           in[(r * 3 + s) * 3 + c] = ok ? __ldg(x + (((long long)b * 3 + c) * H + yi) * W + xi) : 0.f;
       }
-    // the thread's 64 channels go to row threadIdx.x of the tile as 16-byte chunks, chunk c stored at c ^ (row & (NCH-1)):
+    // the thread's row goes to row threadIdx.x of the tile as 16-byte chunks, chunk c stored at c ^ (row & (NCH-1)):
     // a plain [row][channel] layout makes all 32 lanes hit the same bank (row stride = a multiple of 128 bytes)
-    constexpr int NCH = 64 * sizeof(T) / 16;  // 16-byte chunks per row: 16 (fp32) / 8 (bf16)
-    constexpr int PER = 16 / sizeof(T);       // channels per chunk
-    uint4* trow = reinterpret_cast<uint4*>(tile) + threadIdx.x * NCH;
+    uint4* trow = tile + threadIdx.x * NCH;
     const int sw = threadIdx.x & (NCH - 1);
-    if (!any) {
+#pragma unroll 1
+    for (int cv = 0; cv < NV; ++cv) {
+      float a[VN];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        uint4 u;
-        T* e = reinterpret_cast<T*>(&u);
-#pragma unroll
-        for (int j = 0; j < PER; ++j) e[j] = from_float<T>(fmaxf(sb[c * PER + j], 0.f));
-        trow[c ^ sw] = u;
-      }
-    } else {
-#pragma unroll 2
-      for (int c = 0; c < NCH; ++c) {
-        uint4 u;
-        T* e = reinterpret_cast<T*>(&u);
-#pragma unroll
-        for (int q = 0; q < PER; q += 4) {
-          const int c4 = c * PER + q;
-          float a0 = sb[c4], a1 = sb[c4 + 1], a2 = sb[c4 + 2], a3 = sb[c4 + 3];
+      for (int q = 0; q < VN; q += 4) {
+        const int c4 = cv * VN + q;
+        float a0 = sb[c4], a1 = sb[c4 + 1], a2 = sb[c4 + 2], a3 = sb[c4 + 3];
+        if (any) {
 #pragma unroll
           for (int k = 0; k < 27; ++k) {
             const float4 wv = *reinterpret_cast<const float4*>(sw_ + k * 64 + c4);
@@ -99,25 +93,22 @@ __global__ void __launch_bounds__(128) conv1_1_fwd_kernel(const float* __restric
             a2 = fmaf(in[k], wv.z, a2);
             a3 = fmaf(in[k], wv.w, a3);
           }
-          e[q] = from_float<T>(fmaxf(a0, 0.f));
-          e[q + 1] = from_float<T>(fmaxf(a1, 0.f));
-          e[q + 2] = from_float<T>(fmaxf(a2, 0.f));
-          e[q + 3] = from_float<T>(fmaxf(a3, 0.f));
         }
-        trow[c ^ sw] = u;
+        a[q] = fmaxf(a0, 0.f), a[q + 1] = fmaxf(a1, 0.f), a[q + 2] = fmaxf(a2, 0.f), a[q + 3] = fmaxf(a3, 0.f);
       }
+      const typename S::Raw r = S::from_float(a);
+      trow[cv ^ sw] = r.a;
+      if constexpr (sizeof(typename S::Raw) == 32) trow[(cv + NV) ^ sw] = r.b;  // lo plane: chunks NV .. 2 NV - 1
     }
   }
   __syncthreads();
   long long npix = total - p0;
   if (npix > 128) npix = 128;
-  constexpr int NCH2 = 64 * sizeof(T) / 16;
-  const int n16 = (int)(npix * NCH2);
-  uint4* dst = reinterpret_cast<uint4*>(y + p0 * 64);
-  const uint4* src = reinterpret_cast<const uint4*>(tile);
+  const int n16 = (int)(npix * NCH);
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + (size_t)p0 * ROWB);
   for (int i = threadIdx.x; i < n16; i += 128) {
-    const int row = i / NCH2, c = i - row * NCH2;
-    __stcs(dst + i, src[row * NCH2 + (c ^ (row & (NCH2 - 1)))]);
+    const int row = i / NCH, c = i - row * NCH;
+    __stcs(dst + i, tile[row * NCH + (c ^ (row & (NCH - 1)))]);
   }
 }
 
@@ -129,20 +120,32 @@ __global__ void __launch_bounds__(128) conv1_1_fwd_kernel(const float* __restric
 // channels), one shared-memory load and 3 FMAs for its three filter columns.  CTAs are persistent and keep their 3
 // partial sums in registers across all work items: 1728 atomics per CTA in total.
 constexpr int C11_SEG = 64;
+// The split format is staged as fp32 (hi + lo added on the way into shared memory).
 template <typename T>
-__global__ void __launch_bounds__(576) conv1_1_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+struct C11Stage {
+  typedef T type;
+};
+template <>
+struct C11Stage<SplitBf16> {
+  typedef float type;
+};
+template <typename T>
+__global__ void __launch_bounds__(576) conv1_1_wgrad_kernel(const float* __restrict__ x, const void* __restrict__ dy_,
                                                             float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
                                                             int pad, int ylo, int xlo, int wy, int nseg) {
-  constexpr int VN = 16 / sizeof(T);                 // dY elements per 16-byte load
-  constexpr int NV = C11_SEG * 64 / VN;              // 16-byte vectors in one dY tile (64 px x 64 channels, contiguous)
+  constexpr bool SPLIT = sizeof(typename Store<T>::Raw) == 32;
+  typedef typename C11Stage<T>::type ST;             // element type of the staged dY tile
+  constexpr int VN = Store<T>::VN;                   // dY channels per (plane) 16-byte load
+  constexpr int NV = C11_SEG * 64 / VN;              // channel vectors in one dY tile (64 px x 64 channels)
   constexpr int VPT = (NV + 575) / 576;              // vectors per thread
   constexpr int XE = 9 * (C11_SEG + 2), XPT = (XE + 575) / 576;
-  __shared__ __align__(16) T sdy[2][C11_SEG * 64];
+  __shared__ __align__(16) ST sdy[2][C11_SEG * 64];
+  const uint8_t* dy = reinterpret_cast<const uint8_t*>(dy_);
   __shared__ float xs[2][9][C11_SEG + 2];  // [buffer][ci*3 + r][x]: the three input rows under this output row
   const int co = threadIdx.x & 63, cr = threadIdx.x >> 6;  // cr = ci*3 + r
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
   const long long items = (long long)B * wy * nseg;
-  uint4 rdy[VPT];
+  typename Store<T>::Raw rdy[VPT];
   float rx[XPT];
   // software pipeline: the global loads of item i+1 are in flight while item i is reduced out of shared memory
   auto fetch = [&](long long it) {
@@ -152,11 +155,13 @@ __global__ void __launch_bounds__(576) conv1_1_wgrad_kernel(const float* __restr
     const int xo0 = xlo + seg * C11_SEG;
     int npx = Wo - xo0;
     if (npx > C11_SEG) npx = C11_SEG;
-    const uint4* src = reinterpret_cast<const uint4*>(dy + (((long long)b * Ho + yo) * Wo + xo0) * 64);
+    const long long row0 = ((long long)b * Ho + yo) * Wo + xo0;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
-      const int i = threadIdx.x + v * 576;
-      rdy[v] = (i < npx * 64 / VN) ? __ldcs(src + i) : make_uint4(0, 0, 0, 0);  // pixels past the row end count as 0
+      const int i = threadIdx.x + v * 576;  // vector i = pixel i / (64 / VN), channel vector i % (64 / VN)
+      const int px = i / (64 / VN), cv = i - px * (64 / VN);
+      rdy[v] = (px < npx) ? Store<T>::template load_raw<true>(row_ptr<T>(dy, row0 + px, 64), 64, cv)
+                          : Store<T>::zero();  // pixels past the row end count as 0
     }
 #pragma unroll
     for (int v = 0; v < XPT; ++v) {
@@ -177,7 +182,17 @@ __global__ void __launch_bounds__(576) conv1_1_wgrad_kernel(const float* __restr
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
       const int i = threadIdx.x + v * 576;
-      if (i < NV) reinterpret_cast<uint4*>(sdy[buf])[i] = rdy[v];
+      if (i < NV) {
+        if constexpr (SPLIT) {
+          float f[VN];
+          Store<T>::to_float(rdy[v], f);
+          float4* d4 = reinterpret_cast<float4*>(sdy[buf] + i * VN);
+          d4[0] = make_float4(f[0], f[1], f[2], f[3]);
+          d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+        } else {
+          reinterpret_cast<uint4*>(sdy[buf])[i] = rdy[v].a;
+        }
+      }
     }
 #pragma unroll
     for (int v = 0; v < XPT; ++v) {
@@ -186,11 +201,11 @@ __global__ void __launch_bounds__(576) conv1_1_wgrad_kernel(const float* __restr
     }
     __syncthreads();  // double-buffered: nobody still reads this buffer (its previous readers passed the last barrier)
     if (it + gridDim.x < items) fetch(it + gridDim.x);
-    const T* d = sdy[buf] + co;
+    const ST* d = sdy[buf] + co;
     float w0 = xs[buf][cr][0], w1 = xs[buf][cr][1];
 #pragma unroll 16
     for (int px = 0; px < C11_SEG; ++px) {
-      const float dv = as_float<T>(d[px * 64]);
+      const float dv = as_float<ST>(d[px * 64]);
       const float w2 = xs[buf][cr][px + 2];
       acc0 = fmaf(dv, w0, acc0);
       acc1 = fmaf(dv, w1, acc1);
@@ -206,17 +221,12 @@ __global__ void __launch_bounds__(576) conv1_1_wgrad_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// MaxPool2d(2, stride 2, ceil_mode=True) on NHWC, 16-byte channel vectors
+// MaxPool2d(2, stride 2, ceil_mode=True) on NHWC, one channel vector (Store<T>::VN channels) per thread
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-struct Vec16 {
-  static constexpr int N = 16 / sizeof(T);
-  T v[N];
-};
-
-template <typename T>
-__global__ void pool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo) {
-  constexpr int VN = 16 / sizeof(T);
+__global__ void pool_fwd_kernel(const void* __restrict__ in, void* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo) {
+  using S = Store<T>;
+  constexpr int VN = S::VN;
   const int cv = C / VN;
   const long long total = (long long)B * Ho * Wo * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -235,27 +245,26 @@ __global__ void pool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, i
       for (int dx = 0; dx < 2; ++dx) {
         const int y = 2 * yo + dy, x = 2 * xo + dx;
         if (y < H && x < W) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + (((long long)b * H + y) * W + x) * C) + c);
-          const T* e = reinterpret_cast<const T*>(&u);
+          float v[VN];
+          S::to_float(S::template load_raw<false>(row_ptr<T>(in, ((long long)b * H + y) * W + x, C), C, c), v);
 #pragma unroll
-          for (int j = 0; j < VN; ++j) m[j] = fmaxf(m[j], as_float<T>(e[j]));
+          for (int j = 0; j < VN; ++j) m[j] = fmaxf(m[j], v[j]);
         }
       }
-    uint4 o;
-    T* oe = reinterpret_cast<T*>(&o);
-#pragma unroll
-    for (int j = 0; j < VN; ++j) oe[j] = from_float<T>(m[j]);  // values are already representable: exact
-    reinterpret_cast<uint4*>(out + (((long long)b * Ho + yo) * Wo + xo) * C)[c] = o;
+    // tf32 / bf16: the maximum is one of the stored values, re-encoding it is exact.  split: hi + lo of the winner is
+    // re-split, which reproduces the same fp32 value to 2^-17 (the planes themselves may differ in the last bit).
+    S::template store_raw<false>(row_ptr<T>(out, ((long long)b * Ho + yo) * Wo + xo, C), C, c, S::from_float(m));
   }
 }
 
 // dY[b,y,x,c] = dP[b,y/2,x/2,c] if Y[b,y,x,c] is the FIRST maximum of its window (scan order, like ATen) and > 0 (ReLU).
-// One thread = one 2x2 window x one 16-byte channel vector: every byte of Y, dP and dY moves exactly once.
+// One thread = one 2x2 window x one channel vector: every byte of Y, dP and dY moves exactly once.
 template <typename T>
-__global__ void __launch_bounds__(256) pool_bwd_kernel(const T* __restrict__ yin, const T* __restrict__ dp, T* __restrict__ dy,
-                                                       int B, int H, int W, int C, int Ho, int Wo, int relu_gate,
-                                                       float* __restrict__ col_sum) {
-  constexpr int VN = 16 / sizeof(T);
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const void* __restrict__ yin, const void* __restrict__ dp,
+                                                       void* __restrict__ dy, int B, int H, int W, int C, int Ho, int Wo,
+                                                       int relu_gate, float* __restrict__ col_sum) {
+  using S = Store<T>;
+  constexpr int VN = S::VN;
   const int cv = C / VN;
   // per-channel sums of dy (= of the routed dp values that pass the gate): the producer conv's bias gradient.
   // 256 % cv == 0 is guaranteed by the host when col_sum is given, so a thread keeps ONE channel vector for the whole
@@ -271,36 +280,39 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const T* __restrict__ yin
     r /= Wo;
     const int yo = (int)(r % Ho);
     const int b = (int)(r / Ho);
-    uint4 u[4];
+    float yv[4][VN];
     bool have[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int yy = 2 * yo + (q >> 1), xx = 2 * xo + (q & 1);
       have[q] = yy < H && xx < W;
-      u[q] = have[q] ? __ldcs(reinterpret_cast<const uint4*>(yin + (((long long)b * H + yy) * W + xx) * C) + c)
-                     : make_uint4(0, 0, 0, 0);
+      if (have[q]) {
+        S::to_float(S::template load_raw<true>(row_ptr<T>(yin, ((long long)b * H + yy) * W + xx, C), C, c), yv[q]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) yv[q][j] = 0.f;
+      }
     }
-    const uint4 gu = __ldcs(reinterpret_cast<const uint4*>(dp + (((long long)b * Ho + yo) * Wo + xo) * C) + c);
-    const T* ge = reinterpret_cast<const T*>(&gu);
-    uint4 o[4];
+    float g[VN];
+    S::to_float(S::template load_raw<true>(row_ptr<T>(dp, ((long long)b * Ho + yo) * Wo + xo, C), C, c), g);
+    float o[4][VN];
 #pragma unroll
     for (int j = 0; j < VN; ++j) {
       float best = -INFINITY;
       int win = 0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float v = as_float<T>(reinterpret_cast<const T*>(&u[q])[j]);
-        if (have[q] && v > best) best = v, win = q;  // strict >: the first maximum in scan order keeps the gradient
-      }
+      for (int q = 0; q < 4; ++q)
+        if (have[q] && yv[q][j] > best) best = yv[q][j], win = q;  // strict >: the first maximum in scan order keeps the gradient
       const bool pass = !relu_gate || best > 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) reinterpret_cast<T*>(&o[q])[j] = (pass && q == win) ? ge[j] : from_float<T>(0.f);
-      if (pass) csum[j] += as_float<T>(ge[j]);
+      for (int q = 0; q < 4; ++q) o[q][j] = (pass && q == win) ? g[j] : 0.f;
+      if (pass) csum[j] += g[j];
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int yy = 2 * yo + (q >> 1), xx = 2 * xo + (q & 1);
-      if (have[q]) __stcs(reinterpret_cast<uint4*>(dy + (((long long)b * H + yy) * W + xx) * C) + c, o[q]);
+      // g is a stored value: re-encoding it is exact (tf32 / bf16) or the same fp32 value to 2^-17 (split)
+      if (have[q]) S::template store_raw<true>(row_ptr<T>(dy, ((long long)b * H + yy) * W + xx, C), C, c, S::from_float(o[q]));
     }
   }
   if (col_sum) {
@@ -320,13 +332,14 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const T* __restrict__ yin
   }
 }
 
-// db[c] += sum over rows of dy[row][c]   (dy row stride ld).  HBM-bound single pass: a thread owns one 16-byte channel
-// vector and walks rows with a block-wide stride, 4 loads in flight; partial sums meet in shared memory, one atomic per
+// db[c] += sum over rows of dy[row][c]   (dy row stride ld).  HBM-bound single pass: a thread owns one channel vector
+// and walks rows with a block-wide stride, 4 loads in flight; partial sums meet in shared memory, one atomic per
 // (block, channel).
 template <typename T>
-__global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ dy, float* __restrict__ db, long long rows,
+__global__ void __launch_bounds__(256) bias_grad_kernel(const void* __restrict__ dy, float* __restrict__ db, long long rows,
                                                         int C, long long ld, long long rows_per_block) {
-  constexpr int VN = 16 / sizeof(T);
+  using S = Store<T>;
+  constexpr int VN = S::VN;
   __shared__ float red[256 * VN];
   const int cv = (C + VN - 1) / VN;          // channel vectors per row (C % VN == 0 is checked by the host)
   const int lanes = cv < 256 ? cv : 256;      // threads along the channel axis
@@ -343,10 +356,10 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ dy
     if (c < cv && tr < rstep) {
 #pragma unroll 4
       for (long long r = r0 + tr; r < r1; r += rstep) {
-        const uint4 u = __ldcs(reinterpret_cast<const uint4*>(dy + r * ld) + c);
-        const T* e = reinterpret_cast<const T*>(&u);
+        float v[VN];
+        S::to_float(S::template load_raw<true>(row_ptr<T>(dy, r, ld), (int)ld, c), v);
 #pragma unroll
-        for (int j = 0; j < VN; ++j) acc[j] += as_float<T>(e[j]);
+        for (int j = 0; j < VN; ++j) acc[j] += v[j];
       }
     }
 #pragma unroll
@@ -364,15 +377,28 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ dy
   }
 }
 
-// OIHW fp32 -> [O_pad][R*S][I] T   (rows >= O are zero; fp32 values are rounded to tf32)
+// one packed weight element: tf32-rounded fp32, bf16, or (split) bf16 hi at out[i] and lo at out[plane + i]
 template <typename T>
-__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int O, int I, int RS, int O_pad) {
+__device__ __forceinline__ void put_weight(void* out, long long i, long long plane, float v) {
+  if constexpr (sizeof(typename Store<T>::Raw) == 32) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    reinterpret_cast<__nv_bfloat16*>(out)[i] = hi;
+    reinterpret_cast<__nv_bfloat16*>(out)[plane + i] = lo;
+  } else {
+    reinterpret_cast<T*>(out)[i] = from_float<T>(v);
+  }
+}
+
+// OIHW fp32 -> [O_pad][R*S][I] T   (rows >= O are zero; fp32 values are rounded to tf32; split: two such planes, hi then lo)
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, void* __restrict__ out, int O, int I, int RS, int O_pad) {
   const long long total = (long long)O_pad * RS * I;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(i % I);
     const int rs = (int)((i / I) % RS);
     const int o = (int)(i / ((long long)I * RS));
-    out[i] = from_float<T>(o < O ? w[((long long)o * I + ci) * RS + rs] : 0.f);
+    put_weight<T>(out, i, total, o < O ? w[((long long)o * I + ci) * RS + rs] : 0.f);
   }
 }
 // OIHW fp32 -> the transposed layouts the data-gradient GEMMs read (K = output channel, contiguous):
@@ -380,7 +406,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 //   mode 1: out[(r*S+s)*I + ci][co]            dgrad as one GEMM producing per-tap columns (then szn_col2im)
 // co >= O is zero-filled up to O_pad.
 template <typename T>
-__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, int O, int I, int R, int S,
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, void* __restrict__ out, int O, int I, int R, int S,
                                          int O_pad, int mode) {
   const int RS = R * S;
   const long long total = (long long)I * RS * O_pad;
@@ -395,14 +421,15 @@ __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, T* __restr
       tap = (int)(row / I);
       ci = (int)(row - (long long)tap * I);
     }
-    out[i] = from_float<T>(co < O ? w[((long long)co * I + ci) * RS + tap] : 0.f);
+    put_weight<T>(out, i, total, co < O ? w[((long long)co * I + ci) * RS + tap] : 0.f);
   }
 }
 
 // dx[b,Y,X,ci] = sum_{r,s} dcol[b, Y-r, X-s, (r*S+s)*C + ci]   (valid conv, pad 0): the scatter-free transpose of im2col
 template <typename T>
-__global__ void col2im_kernel(const T* __restrict__ dcol, T* __restrict__ dx, int B, int H, int W, int C, int R, int S) {
-  constexpr int VN = 16 / sizeof(T);
+__global__ void col2im_kernel(const void* __restrict__ dcol, void* __restrict__ dx, int B, int H, int W, int C, int R, int S) {
+  using St = Store<T>;
+  constexpr int VN = St::VN;
   const int Ho = H - R + 1, Wo = W - S + 1, cv = C / VN;
   const long long total = (long long)B * H * W * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -421,18 +448,15 @@ __global__ void col2im_kernel(const T* __restrict__ dcol, T* __restrict__ dx, in
       for (int sx = 0; sx < S; ++sx) {
         const int x = X - sx;
         if (x < 0 || x >= Wo) continue;
-        const T* src = dcol + ((((long long)b * Ho + y) * Wo + x) * (R * S) + (r * S + sx)) * C;
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + c);
-        const T* e = reinterpret_cast<const T*>(&u);
+        // a dcol pixel row holds R*S*C channels; this tap's C channels start at channel vector (r*S+sx)*cv
+        float v[VN];
+        St::to_float(St::template load_raw<false>(row_ptr<T>(dcol, ((long long)b * Ho + y) * Wo + x, (long long)R * S * C),
+                                                  R * S * C, (r * S + sx) * cv + c), v);
 #pragma unroll
-        for (int j = 0; j < VN; ++j) acc[j] += as_float<T>(e[j]);
+        for (int j = 0; j < VN; ++j) acc[j] += v[j];
       }
     }
-    uint4 o;
-    T* oe = reinterpret_cast<T*>(&o);
-#pragma unroll
-    for (int j = 0; j < VN; ++j) oe[j] = from_float<T>(acc[j]);
-    reinterpret_cast<uint4*>(dx + (((long long)b * H + Y) * W + X) * C)[c] = o;
+    St::template store_raw<false>(row_ptr<T>(dx, ((long long)b * H + Y) * W + X, C), C, c, St::from_float(acc));
   }
 }
 
@@ -458,11 +482,11 @@ __global__ void dropout_scale_kernel(float* __restrict__ scale, int n, unsigned 
   scale[i] = (z >> 40) & 1ull ? 2.f : 0.f;
 }
 
-// fp32 NCHW/any -> T elementwise (used for casting small tensors)
+// fp32 [rows][C] -> T [rows][C] (used for casting small tensors; the split format needs the row length)
 template <typename T>
-__global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, long long n) {
+__global__ void cast_kernel(const float* __restrict__ in, void* __restrict__ out, long long n, int C) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = from_float<T>(in[i]);
+    Store<T>::store_elem(out, i / C, C, (int)(i % C), in[i]);
 }
 
 // torch.optim.SGD step (train.py:126-129: momentum .99, weight_decay 5e-4, biases lr x2 / no decay), one fused pass:
@@ -534,7 +558,7 @@ using namespace szn;
 
 extern "C" const char* szn_last_error(void) { return g_err; }
 extern "C" long long szn_launch_count(void) { return g_launches; }
-extern "C" int szn_abi_version(void) { return 1; }
+extern "C" int szn_abi_version(void) { return 2; }
 
 #define DISPATCH_T(dtype, CALL)                 \
   do {                                          \
@@ -543,6 +567,9 @@ extern "C" int szn_abi_version(void) { return 1; }
       CALL;                                     \
     } else if ((dtype) == SZN_F32) {            \
       typedef float T;                          \
+      CALL;                                     \
+    } else if ((dtype) == SZN_F32X3) {          \
+      typedef SplitBf16 T;                      \
       CALL;                                     \
     } else {                                    \
       return set_error(SZN_ERR_ARG, "bad dtype"); \
@@ -554,7 +581,7 @@ extern "C" int szn_conv1_1_fwd(int dtype, const float* x, const float* w_oihw, c
   const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
   const long long total = (long long)B * Ho * Wo;
   const unsigned grid = (unsigned)((total + 127) / 128);
-  DISPATCH_T(dtype, (conv1_1_fwd_kernel<T><<<grid, 128, 0, (cudaStream_t)stream>>>(x, w_oihw, bias, (T*)y, B, H, W, Ho, Wo, pad)));
+  DISPATCH_T(dtype, (conv1_1_fwd_kernel<T><<<grid, 128, 0, (cudaStream_t)stream>>>(x, w_oihw, bias, y, B, H, W, Ho, Wo, pad)));
   return check_launch("szn_conv1_1_fwd");
 }
 
@@ -567,23 +594,23 @@ extern "C" int szn_conv1_1_wgrad(int dtype, const float* x, const void* dy, floa
   const int nseg = (wx + C11_SEG - 1) / C11_SEG;
   const long long items = (long long)B * wy * nseg;
   const int grid = (int)(items < 148 * 3 ? items : 148 * 3);
-  DISPATCH_T(dtype, (conv1_1_wgrad_kernel<T><<<grid, 576, 0, (cudaStream_t)stream>>>(x, (const T*)dy, dw_oihw, B, H, W, Ho, Wo, pad, ylo, xlo, wy, nseg)));
+  DISPATCH_T(dtype, (conv1_1_wgrad_kernel<T><<<grid, 576, 0, (cudaStream_t)stream>>>(x, dy, dw_oihw, B, H, W, Ho, Wo, pad, ylo, xlo, wy, nseg)));
   return check_launch("szn_conv1_1_wgrad");
 }
 
 extern "C" int szn_pool_fwd(int dtype, const void* in, void* out, int B, int H, int W, int C, void* stream) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const int vn = dtype == SZN_BF16 ? 8 : 4;
+  const int vn = dtype == SZN_F32 ? 4 : 8;
   if (C % vn) return set_error(SZN_ERR_ARG, "szn_pool_fwd: C must be a multiple of 16 bytes");
   const long long total = (long long)B * Ho * Wo * (C / vn);
-  DISPATCH_T(dtype, (pool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)in, (T*)out, B, H, W, C, Ho, Wo)));
+  DISPATCH_T(dtype, (pool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, Ho, Wo)));
   return check_launch("szn_pool_fwd");
 }
 
 extern "C" int szn_pool_bwd(int dtype, const void* y, const void* dp, void* dy, int B, int H, int W, int C, int relu_gate,
                             float* dy_col_sum, void* stream) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const int vn = dtype == SZN_BF16 ? 8 : 4;
+  const int vn = dtype == SZN_F32 ? 4 : 8;
   if (C % vn) return set_error(SZN_ERR_ARG, "szn_pool_bwd: C must be a multiple of 16 bytes");
   const long long total = (long long)B * Ho * Wo * (C / vn);
   if (dy_col_sum && 256 % (C / vn)) return set_error(SZN_ERR_UNSUPPORTED, "szn_pool_bwd: fused channel sums need C/vector to divide 256");
@@ -596,40 +623,40 @@ extern "C" int szn_pool_bwd(int dtype, const void* y, const void* dp, void* dy, 
     }
     if (dy_col_sum && grid > cap) grid = cap;
   }
-  DISPATCH_T(dtype, (pool_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)y, (const T*)dp, (T*)dy, B, H, W, C, Ho, Wo, relu_gate, dy_col_sum)));
+  DISPATCH_T(dtype, (pool_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(y, dp, dy, B, H, W, C, Ho, Wo, relu_gate, dy_col_sum)));
   return check_launch("szn_pool_bwd");
 }
 
 extern "C" int szn_bias_grad(int dtype, const void* dy, float* db, long long rows, int C, long long ld, void* stream) {
-  const int vn = dtype == SZN_BF16 ? 8 : 4;
+  const int vn = dtype == SZN_F32 ? 4 : 8;
   if (C % vn || ld % vn || (reinterpret_cast<uintptr_t>(dy) & 15))
     return set_error(SZN_ERR_ARG, "szn_bias_grad: C, ld and dy must be 16-byte aligned");
   long long rpb = (rows + 148 * 8 - 1) / (148 * 8);
   if (rpb < 64) rpb = 64;
   const unsigned grid = (unsigned)((rows + rpb - 1) / rpb);
-  DISPATCH_T(dtype, (bias_grad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, db, rows, C, ld, rpb)));
+  DISPATCH_T(dtype, (bias_grad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, db, rows, C, ld, rpb)));
   return check_launch("szn_bias_grad");
 }
 
 extern "C" int szn_pack_weight(int dtype, const float* w_oihw, void* out, int O, int I, int R, int S, int O_pad,
                                void* stream) {
   const long long total = (long long)O_pad * R * S * I;
-  DISPATCH_T(dtype, (pack_weight_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (T*)out, O, I, R * S, O_pad)));
+  DISPATCH_T(dtype, (pack_weight_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, out, O, I, R * S, O_pad)));
   return check_launch("szn_pack_weight");
 }
 
 extern "C" int szn_pack_weight_dgrad(int dtype, const float* w_oihw, void* out, int O, int I, int R, int S, int O_pad,
                                      int mode, void* stream) {
   const long long total = (long long)I * R * S * O_pad;
-  DISPATCH_T(dtype, (pack_weight_dgrad_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (T*)out, O, I, R, S, O_pad, mode)));
+  DISPATCH_T(dtype, (pack_weight_dgrad_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, out, O, I, R, S, O_pad, mode)));
   return check_launch("szn_pack_weight_dgrad");
 }
 
 extern "C" int szn_col2im(int dtype, const void* dcol, void* dx, int B, int H, int W, int C, int R, int S, void* stream) {
-  const int vn = dtype == SZN_BF16 ? 8 : 4;
+  const int vn = dtype == SZN_F32 ? 4 : 8;
   if (C % vn) return set_error(SZN_ERR_ARG, "szn_col2im: C must be a multiple of 16 bytes");
   const long long total = (long long)B * H * W * (C / vn);
-  DISPATCH_T(dtype, (col2im_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dcol, (T*)dx, B, H, W, C, R, S)));
+  DISPATCH_T(dtype, (col2im_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dcol, dx, B, H, W, C, R, S)));
   return check_launch("szn_col2im");
 }
 
@@ -666,7 +693,8 @@ extern "C" int szn_adam_step(float* param, const float* grad, float* exp_avg, fl
   return check_launch("szn_adam_step");
 }
 
-extern "C" int szn_cast(int dtype, const float* in, void* out, long long n, void* stream) {
-  DISPATCH_T(dtype, (cast_kernel<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, (T*)out, n)));
+extern "C" int szn_cast(int dtype, const float* in, void* out, long long rows, int C, void* stream) {
+  const long long n = rows * C;
+  DISPATCH_T(dtype, (cast_kernel<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n, C)));
   return check_launch("szn_cast");
 }

@@ -22,6 +22,11 @@
 // descriptors, fp32 accumulators in TMEM (two buffers: the epilogue of a tile overlaps the next main loop).
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
 // (TMEM -> registers -> swizzled staging rows -> TMA store / reduce-add).  192 threads, one CTA per SM.
+//
+// SPLIT (dtype SZN_F32X3, "fp32-grade"): every operand arrives as two bf16 planes hi / lo (szn_store.cuh); a stage holds
+// A_hi | A_lo | B_hi | B_lo and every K step issues three kind::f16 MMAs hi*hi + lo*hi + hi*lo into the same fp32
+// accumulator (the lo*lo term is below 2^-18 of the product).  The epilogue splits its fp32 results into the two output
+// planes again.  Same bytes per element as the tf32 path, 1.5x its MMA time, ~2^-16 instead of 2^-11 per product.
 #include "szn_internal.h"
 #include "szn_ptx.cuh"
 #include <stdlib.h>
@@ -43,9 +48,12 @@ struct UmmaParams {
   int m_fast;  // MODE 0: tile order (0: N tiles fastest, share A through L2; 1: M tiles fastest, share the weight slice)
   int mpair;  // MODE 2: 128-row output sub-tiles per work item (2: two accumulators share every B stage)
   int nbuf;   // accumulator buffers in TMEM (2 unless one tile needs all 512 columns)
-  int nacc, acc_cols;  // accumulators per tile (K steps round-robin over them) and their TMEM column stride
+  int acc_cols;  // TMEM column stride between the accumulators of a tile (MODE 2 tile pairs, MODE 0 nacc = 2)
+  int nacc;      // MODE 0: accumulators per tile (see launch(): shorter fp32 accumulation chains), summed by the epilogue
   int gpt, b_boxes, ksteps;  // MODE 2: 128-byte column groups per B box, B boxes per stage, MMAs (K steps) per stage
-  long long ldo;          // row stride of the output, elements (mask_ref shares it)
+  long long ldo;          // channels per output row (= its row stride in elements; split: stride of one plane pair / 2)
+  long long ld_mask;      // row stride of mask_ref in elements of T (split: 2 * channels, the hi plane comes first)
+  int a_lo_goff, b_lo_goff;  // SPLIT, MODE 2: channel-group offset of the lo plane inside a pixel row of dy / x
   const float* bias;      // [N] or null
   const float* scale;     // [B][scale_ld] per-(image, channel) multiplier (Dropout2d) or null
   int scale_ld;
@@ -129,11 +137,13 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) 
 //                                                       overlaps the main loop of tile i+1)
 //   staging     cp.async.bulk groups   epilogue      -> TMA store (two 16 KB swizzled buffers; coalesced, clipped by
 //                                                       the tensor map, fp32 add-reduction for the split-K wgrad)
-template <typename T, int MODE>
+template <typename T, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(192, 1)
 umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const UmmaParams p) {
+  static_assert(!SPLIT || sizeof(T) == 2, "the split format is made of bf16 planes");
   constexpr bool TF32 = sizeof(T) == 4;
+  constexpr int NPL = SPLIT ? 2 : 1;        // operand planes per stage
   constexpr int KC = 128 / (int)sizeof(T);  // contraction elements per stage
   constexpr int UK = KC / 4;                // UMMA K (16 bf16 / 8 tf32): 4 MMAs per stage
   constexpr int A_BYTES = 128 * 128;
@@ -147,8 +157,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int block_n = p.block_n;
   const int mp = (MODE == 2) ? p.mpair : 1;
-  const int a_bytes = A_BYTES * mp;
-  const int stage_bytes = a_bytes + block_n * 128;
+  const int a_bytes = A_BYTES * mp;          // one plane of A
+  const int b_bytes = block_n * 128;          // one plane of B
+  const int stage_bytes = NPL * (a_bytes + b_bytes);  // A_hi | A_lo | B_hi | B_lo
   const int stages = p.stages;
   uint8_t* staging = smem + stages * stage_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(staging + 2 * STAGING_BYTES);
@@ -225,17 +236,29 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&empty[s], ph ^ 1u);
         if (elect_one()) {
           uint8_t* a_dst = smem + s * stage_bytes;
-          uint8_t* b_dst = a_dst + a_bytes;
-          mbar_expect_tx(&full[s], a_tx + b_tx);
+          uint8_t* b_dst = a_dst + NPL * a_bytes;
+          mbar_expect_tx(&full[s], NPL * (a_tx + b_tx));
           if (MODE == 0) {
-            tma_load_4d(a_dst, &tmA, &full[s], cc * KC, t.x0 + sx - p.pad, t.y0 + r - p.pad, t.b);
-            tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0);
+            if (SPLIT) {  // planes are the 5th (A) / 3rd (B) tensor-map dimension
+              tma_load_5d(a_dst, &tmA, &full[s], cc * KC, t.x0 + sx - p.pad, t.y0 + r - p.pad, t.b, 0);
+              tma_load_5d(a_dst + a_bytes, &tmA, &full[s], cc * KC, t.x0 + sx - p.pad, t.y0 + r - p.pad, t.b, 1);
+              tma_load_3d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0, 0);
+              tma_load_3d(b_dst + b_bytes, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0, 1);
+            } else {
+              tma_load_4d(a_dst, &tmA, &full[s], cc * KC, t.x0 + sx - p.pad, t.y0 + r - p.pad, t.b);
+              tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0);
+            }
           } else {
             tma_load_5d(a_dst, &tmA, &full[s], 0, px0, py0, bb, t.m0 / KC);
+            if (SPLIT) tma_load_5d(a_dst + a_bytes, &tmA, &full[s], 0, px0, py0, bb, p.a_lo_goff + t.m0 / KC);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (j < n_bbox)
+              if (j < n_bbox) {
                 tma_load_5d(b_dst + j * box_tx, &tmB, &full[s], 0, px0 + g_dx[j], py0 + g_dy[j], bb, g_cg[j]);
+                if (SPLIT)
+                  tma_load_5d(b_dst + b_bytes + j * box_tx, &tmB, &full[s], 0, px0 + g_dx[j], py0 + g_dy[j], bb,
+                              p.b_lo_goff + g_cg[j]);
+              }
           }
         }
         __syncwarp();
@@ -274,7 +297,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_addr = a_addr + a_bytes;
+          const uint32_t b_addr = a_addr + NPL * a_bytes;
           // K-major: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzled row.
           // MN-major: 128 B-wide column groups LBO = rows_a*128 B apart (as the 5-D TMA box lays them down), K advances UK
           // rows of 128 B per MMA; the K rows come in groups SBO apart: 8 rows / 1024 B for 16-bit operands (SWIZZLE_128B),
@@ -283,7 +306,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t lbo = (uint32_t)rows_a * 128u;
           const int ksteps = (MODE == 2) ? p.ksteps : 4;
           if (MODE == 2 && mp == 2) {
-            // two 128-row sub-tiles share the B stage
+            // two 128-row sub-tiles share the B stage (never with SPLIT: the stage would not fit)
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t adesc = umma_desc(a_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT);
               const uint64_t adesc2 = umma_desc(a_addr + (128 / KC) * lbo + k * UK * 128, lbo, MN_SBO, MN_LAYOUT);
@@ -293,14 +316,27 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           } else {
             for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc = A_MN ? umma_desc(a_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
-                                          : umma_desc_sw128(a_addr + k * 32, 16, 1024);
-              const uint64_t bdesc = B_MN ? umma_desc(b_addr + k * UK * 128, lbo, MN_SBO, MN_LAYOUT)
-                                          : umma_desc_sw128(b_addr + k * 32, 16, 1024);
-              // narrow tiles rotate their K steps over 2-4 accumulators that the epilogue adds (consecutive MMAs into
-              // ONE accumulator serialise on its read-modify-write)
-              const int a = k & (p.nacc - 1);
-              tc_mma<TF32>(dacc + (uint32_t)(a * p.acc_cols), adesc, bdesc, idesc, (uint32_t)(it != 0 || k >= p.nacc));
+              const uint32_t ao = A_MN ? (uint32_t)(k * UK * 128) : (uint32_t)(k * 32);
+              const uint32_t bo = B_MN ? (uint32_t)(k * UK * 128) : (uint32_t)(k * 32);
+              const uint64_t adesc = A_MN ? umma_desc(a_addr + ao, lbo, MN_SBO, MN_LAYOUT) : umma_desc_sw128(a_addr + ao, 16, 1024);
+              const uint64_t bdesc = B_MN ? umma_desc(b_addr + bo, lbo, MN_SBO, MN_LAYOUT) : umma_desc_sw128(b_addr + bo, 16, 1024);
+              // The tensor core's fp32 accumulate truncates: every MMA into an accumulator loses up to one ulp OF THE
+              // ACCUMULATOR, towards zero, so a chain of n MMAs comes out short by ~n * 2^-24 (fc6, K = 25088: 2e-4).
+              // With a second accumulator (nacc = 2) the split format keeps its two small correction terms apart from the
+              // hi*hi chain (3x fewer truncations at full magnitude), the other formats alternate K steps (2x fewer).
+              if (SPLIT) {  // hi*hi  +  (A_lo * B_hi + A_hi * B_lo)
+                const uint64_t adesc_lo = A_MN ? umma_desc(a_addr + a_bytes + ao, lbo, MN_SBO, MN_LAYOUT)
+                                               : umma_desc_sw128(a_addr + a_bytes + ao, 16, 1024);
+                const uint64_t bdesc_lo = B_MN ? umma_desc(b_addr + b_bytes + bo, lbo, MN_SBO, MN_LAYOUT)
+                                               : umma_desc_sw128(b_addr + b_bytes + bo, 16, 1024);
+                const uint32_t dcorr = dacc + (uint32_t)((p.nacc - 1) * p.acc_cols);
+                tc_mma<TF32>(dacc, adesc, bdesc, idesc, (uint32_t)((it | k) != 0));
+                tc_mma<TF32>(dcorr, adesc_lo, bdesc, idesc, (uint32_t)(p.nacc == 1 || (it | k) != 0));
+                tc_mma<TF32>(dcorr, adesc, bdesc_lo, idesc, 1u);
+              } else {
+                const int a = k & (p.nacc - 1);
+                tc_mma<TF32>(dacc + (uint32_t)(a * p.acc_cols), adesc, bdesc, idesc, (uint32_t)(it != 0 || k >= p.nacc));
+              }
             }
           }
           tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
@@ -321,6 +357,28 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q4 * 32 + lane;
     const bool issuer = elect_one() && warp == 2;  // one fixed lane of warp 2 owns the bulk-store groups
     uint32_t local = 0, chunk_ctr = 0;
+
+    // one 128 x 128-byte tile: registers -> swizzled staging rows -> TMA store / reduce-add.  Two staging buffers: the
+    // store issued from a buffer two tiles ago must have read it before it is overwritten.
+    // SWIZZLE_128B: 16-byte chunk j of row r lives at chunk (j ^ (r & 7)); conflict-free for a warp's 32 rows
+    auto emit = [&](const uint4 (&q)[8], int nb, int m_row, const TileCoord& t, int plane) {
+      uint8_t* sbuf = staging + (chunk_ctr & 1u) * STAGING_BYTES;
+      ++chunk_ctr;
+      if (issuer) bulk_wait_read<1>();
+      named_bar_sync(1, 128);
+      uint4* srow = reinterpret_cast<uint4*>(sbuf + row * 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) srow[j ^ (row & 7)] = q[j];
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (issuer) {
+        if (MODE == 2) tma_reduce_add_2d(&tmO, sbuf, nb, m_row);
+        else if (SPLIT && !f32_out) tma_store_5d(&tmO, sbuf, nb, t.x0, t.y0, t.b, plane);
+        else tma_store_4d(&tmO, sbuf, nb, t.x0, t.y0, t.b);
+        bulk_commit();
+      }
+    };
+
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<MODE>(p, tile);
       if (t.n_iters == 0) continue;
@@ -351,12 +409,13 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float f[CWMAX];
         {
           uint32_t v[32];
+          const bool two = MODE != 2 && p.nacc == 2;  // second accumulator of the tile (see the MMA issuer)
           tmem_ld32(tb + (uint32_t)c0, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          for (int a = 1; a < p.nacc; ++a) {  // partial sums of the other accumulators
-            tmem_ld32(tb + (uint32_t)(a * p.acc_cols + c0), v);
+          if (two) {
+            tmem_ld32(tb + (uint32_t)(p.acc_cols + c0), v);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
@@ -368,13 +427,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[(32 + j) % CWMAX] = f32_out ? 0.f : __uint_as_float(v[j]);
-            if (!f32_out) {
-              for (int a = 1; a < p.nacc; ++a) {
-                tmem_ld32(tb + (uint32_t)(a * p.acc_cols + c0 + 32), v);
-                tmem_ld_wait();
+            if (two && !f32_out) {
+              tmem_ld32(tb + (uint32_t)(p.acc_cols + c0 + 32), v);
+              tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[(32 + j) % CWMAX] += __uint_as_float(v[j]);
-              }
+              for (int j = 0; j < 32; ++j) f[(32 + j) % CWMAX] += __uint_as_float(v[j]);
             }
           }
         }
@@ -405,7 +462,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < CWMAX; ++j) f[j] *= sv[j];
           }
           if (p.mask_ref && ok) {
-            const T* ref = reinterpret_cast<const T*>(p.mask_ref) + orow * p.ldo + nb;
+            // ReLU gate: the sign of the stored activation (split: of its hi plane, which has the sign of the value)
+            const T* ref = reinterpret_cast<const T*>(p.mask_ref) + orow * p.ld_mask + nb;
             if (nvalid == CW) {
               const uint4* r4 = reinterpret_cast<const uint4*>(ref);  // 128 contiguous bytes of this thread's row
               if (TF32) {
@@ -439,11 +497,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        // ---- registers -> swizzled staging row -> TMA store ----
-        uint8_t* sbuf = staging + (chunk_ctr & 1u) * STAGING_BYTES;
-        ++chunk_ctr;
-        if (issuer) bulk_wait_read<1>();  // the store issued from this buffer two chunks ago has read it
-        named_bar_sync(1, 128);
+        // ---- registers -> staging -> TMA store ----
         uint4 q[8];
         if (f32_out) {
           if (TF32 && MODE != 2 && !p.out_fp32) {
@@ -454,39 +508,49 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 8; ++j)
             q[j] = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
                               __float_as_uint(f[4 * j + 3]));
+          emit(q, nb, t.m0 + h * 128, t, 0);
         } else {
+          // bf16 output; SPLIT: the hi plane now, the lo plane (the rounding residuals) right after it
+          float res[CWMAX];  // SPLIT only: what the hi plane's rounding left over
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[(8 * j + 0) % CWMAX], f[(8 * j + 1) % CWMAX]);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(f[(8 * j + 2) % CWMAX], f[(8 * j + 3) % CWMAX]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[(8 * j + 4) % CWMAX], f[(8 * j + 5) % CWMAX]);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(f[(8 * j + 6) % CWMAX], f[(8 * j + 7) % CWMAX]);
-            q[j].x = *reinterpret_cast<uint32_t*>(&h0);
-            q[j].y = *reinterpret_cast<uint32_t*>(&h1);
-            q[j].z = *reinterpret_cast<uint32_t*>(&h2);
-            q[j].w = *reinterpret_cast<uint32_t*>(&h3);
-            if (MODE != 2 && p.col_sum) {  // the column sums must see exactly the values that are stored
-              f[(8 * j + 0) % CWMAX] = __low2float(h0), f[(8 * j + 1) % CWMAX] = __high2float(h0);
-              f[(8 * j + 2) % CWMAX] = __low2float(h1), f[(8 * j + 3) % CWMAX] = __high2float(h1);
-              f[(8 * j + 4) % CWMAX] = __low2float(h2), f[(8 * j + 5) % CWMAX] = __high2float(h2);
-              f[(8 * j + 6) % CWMAX] = __low2float(h3), f[(8 * j + 7) % CWMAX] = __high2float(h3);
+            __nv_bfloat162 h2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i0 = (8 * j + 2 * e) % CWMAX, i1 = (8 * j + 2 * e + 1) % CWMAX;
+              h2[e] = __floats2bfloat162_rn(f[i0], f[i1]);
+              if (SPLIT) {
+                res[i0] = f[i0] - __low2float(h2[e]);
+                res[i1] = f[i1] - __high2float(h2[e]);
+              } else if (MODE != 2 && p.col_sum) {  // the column sums must see exactly the values that are stored
+                f[i0] = __low2float(h2[e]), f[i1] = __high2float(h2[e]);
+              }
             }
+            q[j].x = *reinterpret_cast<uint32_t*>(&h2[0]);
+            q[j].y = *reinterpret_cast<uint32_t*>(&h2[1]);
+            q[j].z = *reinterpret_cast<uint32_t*>(&h2[2]);
+            q[j].w = *reinterpret_cast<uint32_t*>(&h2[3]);
+          }
+          emit(q, nb, 0, t, 0);
+          if (SPLIT) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 l2[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                l2[e] = __floats2bfloat162_rn(res[(8 * j + 2 * e) % CWMAX], res[(8 * j + 2 * e + 1) % CWMAX]);
+              q[j].x = *reinterpret_cast<uint32_t*>(&l2[0]);
+              q[j].y = *reinterpret_cast<uint32_t*>(&l2[1]);
+              q[j].z = *reinterpret_cast<uint32_t*>(&l2[2]);
+              q[j].w = *reinterpret_cast<uint32_t*>(&l2[3]);
+            }
+            emit(q, nb, 0, t, 1);
           }
         }
-        // SWIZZLE_128B: 16-byte chunk j of row r lives at chunk (j ^ (r & 7)); conflict-free for a warp's 32 rows
-        uint4* srow = reinterpret_cast<uint4*>(sbuf + row * 128);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) srow[j ^ (row & 7)] = q[j];
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (issuer) {
-          if (MODE == 2) tma_reduce_add_2d(&tmO, sbuf, nb, t.m0 + h * 128);
-          else tma_store_4d(&tmO, sbuf, nb, t.x0, t.y0, t.b);
-          bulk_commit();
-        }
         if (MODE != 2 && p.col_sum) {
-          // bias gradient of the layer that produced this dY: column sums of the stored tile.  Butterfly transpose-reduce:
-          // after 31 shuffles lane l holds the sum over the warp's 32 rows of column l; one RED per (warp, column).
+          // bias gradient of the layer that produced this dY: column sums of the stored tile (split: of hi + lo up to the
+          // 2^-17 of the second rounding).  Butterfly transpose-reduce: after 31 shuffles lane l holds the sum over the
+          // warp's 32 rows of column l; one RED per (warp, column).
           const bool row_live = ok;
 #pragma unroll
           for (int half = 0; half < CWMAX / 32; ++half) {
@@ -607,35 +671,52 @@ static int num_sms() {
   return n;
 }
 
-template <typename T, int MODE>
+template <typename T, int MODE, bool SPLIT>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, UmmaParams& p, long long tiles,
                   cudaStream_t st) {
-  const int stage_bytes = 128 * 128 * (MODE == 2 && p.mpair == 2 ? 2 : 1) + p.block_n * 128;
+  if (MODE != 2 || p.mpair < 1 || SPLIT) p.mpair = 1;
+  const int stage_bytes = (SPLIT ? 2 : 1) * (128 * 128 * p.mpair + p.block_n * 128);
   const int fixed = 2 * 128 * 128 /* epilogue staging */ + 1024 /* alignment */ + 256 /* barriers */;
   int stages = (227 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
+  if (stages < 2) return set_error(SZN_ERR_UNSUPPORTED, "conv: tile does not leave two pipeline stages");
   p.stages = stages;
   p.acc_cols = tmem_cols_for(p.block_n);
-  p.nacc = p.acc_cols <= 64 ? 4 : p.acc_cols == 128 ? 2 : 1;
-  if (MODE != 2 || p.mpair < 1) p.mpair = 1;
-  p.tmem_cols = p.acc_cols * p.nacc * p.mpair;  // per accumulator buffer
+  // second accumulator (shorter truncating fp32 chains, see the MMA issuer): whenever TMEM still holds two buffers of
+  // two; for 256-column tiles only when the main loop is so long (fc6: 392 stages) that giving up the overlap of a
+  // tile's epilogue with the next main loop costs nothing measurable
+  p.nacc = 1;
+  if (MODE == 0) {
+    const int n_iters = p.R * p.S * p.kchunks;
+    if (4 * p.acc_cols <= 512 && (SPLIT || n_iters >= 64)) p.nacc = 2;
+    else if (2 * p.acc_cols <= 512 && n_iters >= 256) p.nacc = 2;
+  }
+  p.tmem_cols = p.acc_cols * p.mpair * p.nacc;  // per accumulator buffer
   p.nbuf = 2 * p.tmem_cols <= 512 ? 2 : 1;
   p.total_tiles = (int)tiles;
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(umma_conv_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<T, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
     if (e != cudaSuccess) return set_error(SZN_ERR_CUDA, cudaGetErrorString(e));
     attr_set = true;
   }
   // persistent: one CTA per SM walks the tile list
   const unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
-  umma_conv_kernel<T, MODE><<<grid, 192, smem, st>>>(a, b, o, p);
+  umma_conv_kernel<T, MODE, SPLIT><<<grid, 192, smem, st>>>(a, b, o, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SZN_ERR_CUDA, cudaGetErrorString(e));
   count_launch();
   return 0;
+}
+
+template <int MODE>
+static int launch_dtype(int dtype, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, UmmaParams& p,
+                        long long tiles, cudaStream_t st) {
+  if (dtype == SZN_BF16) return launch<__nv_bfloat16, MODE, false>(a, b, o, p, tiles, st);
+  if (dtype == SZN_F32X3) return launch<__nv_bfloat16, MODE, true>(a, b, o, p, tiles, st);
+  return launch<float, MODE, false>(a, b, o, p, tiles, st);
 }
 
 // shrink the N tile while the launch would leave SMs idle (fewer CTAs than SMs), keeping N % block_n == 0
@@ -673,8 +754,12 @@ using namespace szn;
 static int conv_gemm(int dtype, const void* x, long long ldx, const void* wt, const float* bias, void* y, int B, int H,
                      int W, int Cin, int Cout, int R, int S, int pad, int relu, const float* scale, int scale_ld,
                      int out_fp32, long long ldo, const void* mask_ref, float* col_sum, void* stream) {
-  const int KC = dtype == SZN_BF16 ? 64 : 32;
+  if (dtype != SZN_F32 && dtype != SZN_BF16 && dtype != SZN_F32X3) return set_error(SZN_ERR_ARG, "conv: bad dtype");
+  const bool split = dtype == SZN_F32X3;
+  const int edt = dtype == SZN_F32 ? SZN_F32 : SZN_BF16;  // element type of one operand plane
+  const int KC = edt == SZN_BF16 ? 64 : 32;
   if (Cin % KC && !(R == 1 && S == 1)) return set_error(SZN_ERR_ARG, "conv: channels per tap must be a multiple of 128 bytes");
+  if (split && (Cin % 8 || ldx % 8 || ldo % 8)) return set_error(SZN_ERR_ARG, "conv (split): planes must be 16-byte aligned");
   int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
   if (Ho <= 0 || Wo <= 0) return set_error(SZN_ERR_ARG, "conv: empty output");
   UmmaParams p{};
@@ -695,19 +780,22 @@ static int conv_gemm(int dtype, const void* x, long long ldx, const void* wt, co
   p.ldo = ldo, p.bias = bias, p.scale = scale, p.scale_ld = scale_ld, p.relu = relu, p.out_fp32 = out_fp32;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(scale)) & 15) == 0 && scale_ld % 4 == 0;
   p.mask_ref = mask_ref;
+  p.ld_mask = split ? 2 * ldo : ldo;
   p.col_sum = col_sum;
   CUtensorMap ta, tb, to;
   {
-    long long od[4] = {Cout, Wo, Ho, Bq}, os[4] = {1, ldo, (long long)Wo * ldo, (long long)Ho * Wo * ldo};
-    int obx[4] = {out_f32 ? 32 : 64, p.TW, p.TH, 1};
-    if (int e = make_tmap(&to, out_f32 ? SZN_F32 : SZN_BF16, y, 4, od, os, obx)) return e;
-    long long d[4] = {Cin, Wq, Hq, Bq}, s[4] = {1, ldx, (long long)Wq * ldx, (long long)Hq * Wq * ldx};
-    int bx[4] = {KC, p.TW, p.TH, 1};
-    if (int e = make_tmap(&ta, dtype, x, 4, d, s, bx)) return e;
+    // split: a pixel row is [hi | lo], i.e. twice the row pitch with the plane as one more (outermost) dimension
+    const long long opitch = (split && !out_f32) ? 2 * ldo : ldo, xpitch = split ? 2 * ldx : ldx;
+    long long od[5] = {Cout, Wo, Ho, Bq, 2}, os[5] = {1, opitch, (long long)Wo * opitch, (long long)Ho * Wo * opitch, ldo};
+    int obx[5] = {out_f32 ? 32 : 64, p.TW, p.TH, 1, 1};
+    if (int e = make_tmap(&to, out_f32 ? SZN_F32 : SZN_BF16, y, (split && !out_f32) ? 5 : 4, od, os, obx)) return e;
+    long long d[5] = {Cin, Wq, Hq, Bq, 2}, s[5] = {1, xpitch, (long long)Wq * xpitch, (long long)Hq * Wq * xpitch, ldx};
+    int bx[5] = {KC, p.TW, p.TH, 1, 1};
+    if (int e = make_tmap(&ta, edt, x, split ? 5 : 4, d, s, bx)) return e;
     long long K = (long long)R * S * Cin;
-    long long d2[2] = {K, Cout}, s2[2] = {1, K};
-    int bx2[2] = {KC, p.block_n};
-    if (int e = make_tmap(&tb, dtype, wt, 2, d2, s2, bx2)) return e;
+    long long d2[3] = {K, Cout, 2}, s2[3] = {1, K, (long long)Cout * K};  // split: hi plane, then lo plane
+    int bx2[3] = {KC, p.block_n, 1};
+    if (int e = make_tmap(&tb, edt, wt, split ? 3 : 2, d2, s2, bx2)) return e;
   }
   const long long tiles = (long long)p.tiles_x * p.tiles_y * Bq * p.n_tiles;
   {
@@ -718,8 +806,7 @@ static int conv_gemm(int dtype, const void* x, long long ldx, const void* wt, co
     const double w_bytes = (double)R * S * Cin * Cout * es, a_bytes = (double)B * H * W * Cin * es;
     p.m_fast = (w_bytes > 96e6 && a_bytes < 64e6 && p.n_tiles > 1) ? 1 : 0;
   }
-  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 0>(ta, tb, to, p, tiles, (cudaStream_t)stream)
-                           : launch<float, 0>(ta, tb, to, p, tiles, (cudaStream_t)stream);
+  return launch_dtype<0>(dtype, ta, tb, to, p, tiles, (cudaStream_t)stream);
 }
 
 extern "C" int szn_conv_fwd(int dtype, const void* x, const void* wt, const float* bias, void* y, int B, int H, int W,
@@ -763,7 +850,10 @@ static void pick_tile_k(int W, int H, int max_rows, int step, int* TW, int* TH) 
 
 extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* dw, int B, int H, int W, int Cin,
                               int Cout, int R, int S, int pad, long long ld_dy, void* stream) {
-  const int KC = dtype == SZN_BF16 ? 64 : 32, UK = KC / 4;
+  if (dtype != SZN_F32 && dtype != SZN_BF16 && dtype != SZN_F32X3) return set_error(SZN_ERR_ARG, "szn_conv_wgrad: bad dtype");
+  const bool split = dtype == SZN_F32X3;
+  const int edt = dtype == SZN_F32 ? SZN_F32 : SZN_BF16;
+  const int KC = edt == SZN_BF16 ? 64 : 32, UK = KC / 4;
   if (Cin % KC || Cout % KC || ld_dy % KC)
     return set_error(SZN_ERR_ARG, "szn_conv_wgrad: Cin, Cout and ld_dy must be multiples of 128 bytes");
   int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
@@ -797,7 +887,7 @@ extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* d
   {
     static int no_pair = -1;
     if (no_pair < 0) no_pair = getenv("SZN_NO_MPAIR") ? 1 : 0;
-    p.mpair = (!no_pair && Cout >= 256 && p.block_n == 256) ? 2 : 1;
+    p.mpair = (!no_pair && !split && Cout >= 256 && p.block_n == 256) ? 2 : 1;
   }
   p.m_tiles = ceil_div(Cout, 128 * p.mpair);
   const long long total_q = (long long)p.tiles_x * p.tiles_y * Bq;
@@ -820,17 +910,19 @@ extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* d
     long long od[2] = {p.N, Cout}, os[2] = {1, p.N};
     int obx[2] = {32, 128};
     if (int e = make_tmap(&to, SZN_F32, dw, 2, od, os, obx)) return e;
-    // 5-D views {KC channels, W, H, B, channel group}: one box fetches several 128-byte channel groups of a pixel patch
-    long long d[5] = {KC, Wo, Ho, Bq, Cout / KC};
-    long long s[5] = {1, ld_dy, (long long)Wo * ld_dy, (long long)Ho * Wo * ld_dy, KC};
+    // 5-D views {KC channels, W, H, B, channel group}: one box fetches several 128-byte channel groups of a pixel patch.
+    // split: a pixel row is [hi | lo]; the lo plane's groups simply follow the hi plane's at a_lo_goff / b_lo_goff.
+    const long long ypitch = split ? 2 * ld_dy : ld_dy, xpitch = split ? 2 * (long long)Cin : Cin;
+    p.a_lo_goff = (int)(ld_dy / KC), p.b_lo_goff = Cin / KC;
+    long long d[5] = {KC, Wo, Ho, Bq, split ? p.a_lo_goff + Cout / KC : Cout / KC};
+    long long s[5] = {1, ypitch, (long long)Wo * ypitch, (long long)Ho * Wo * ypitch, KC};
     int bx[5] = {KC, p.TW, p.TH, 1, (128 / KC) * p.mpair};
-    if (int e = make_tmap(&ta, dtype, dy, 5, d, s, bx, true)) return e;
-    long long d2[5] = {KC, Wq, Hq, Bq, Cin / KC};
-    long long s2[5] = {1, Cin, (long long)Wq * Cin, (long long)Hq * Wq * Cin, KC};
+    if (int e = make_tmap(&ta, edt, dy, 5, d, s, bx, true)) return e;
+    long long d2[5] = {KC, Wq, Hq, Bq, (split ? 2 : 1) * Cin / KC};
+    long long s2[5] = {1, xpitch, (long long)Wq * xpitch, (long long)Hq * Wq * xpitch, KC};
     int bx2[5] = {KC, p.TW, p.TH, 1, p.gpt};
-    if (int e = make_tmap(&tb, dtype, x, 5, d2, s2, bx2, true)) return e;
+    if (int e = make_tmap(&tb, edt, x, 5, d2, s2, bx2, true)) return e;
   }
   const long long grid = tiles * p.splits;
-  return dtype == SZN_BF16 ? launch<__nv_bfloat16, 2>(ta, tb, to, p, grid, (cudaStream_t)stream)
-                           : launch<float, 2>(ta, tb, to, p, grid, (cudaStream_t)stream);
+  return launch_dtype<2>(dtype, ta, tb, to, p, grid, (cudaStream_t)stream);
 }

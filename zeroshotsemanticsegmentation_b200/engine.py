@@ -36,7 +36,16 @@ PARAM_ORDER = [n + s for n in CONV_NAMES for s in (".weight", ".bias")] + [
     "score_fr.weight", "score_fr.bias", "seenmask_score.weight", "seenmask_score.bias",
     "upscore.weight", "seenmask_upscore.weight"]
 
-PRECISIONS = {"tf32": (_lib.F32, torch.float32), "bf16": (_lib.BF16, torch.bfloat16)}
+# precision -> (C-ABI dtype code, torch dtype of the trunk tensors).  "fp32" is the fp32-grade mode: every activation /
+# data gradient / packed weight is stored as two bf16 planes (hi, lo) -- a pixel row of C channels is a bf16 row of 2C
+# elements, the 4C bytes an fp32 row would take -- and every product is hi*hi + lo*hi + hi*lo on the bf16 tensor cores.
+PRECISIONS = {"tf32": (_lib.F32, torch.float32), "bf16": (_lib.BF16, torch.bfloat16),
+              "fp32": (_lib.F32X3, torch.bfloat16)}
+
+
+def planes(dt):
+    """bf16 planes per stored value (2 for the split fp32-grade format)."""
+    return 2 if dt == _lib.F32X3 else 1
 
 
 def round_up(a, b):
@@ -62,7 +71,7 @@ def _pack(dt, tdtype, w, o_pad=None):
     w = w.contiguous()  # parameters may be channels_last (models._use_kernel_weight_layout); the pack kernels read OIHW
     O, I, R, S = w.shape
     o_pad = O if o_pad is None else o_pad
-    out = torch.empty((o_pad, R * S, I), device=w.device, dtype=tdtype)
+    out = torch.empty((planes(dt) * o_pad, R * S, I), device=w.device, dtype=tdtype)  # split: hi plane, then lo plane
     call("szn_pack_weight", dt, ptr(w), ptr(out), O, I, R, S, o_pad, _lib.stream())
     return out
 
@@ -72,7 +81,7 @@ def _pack_d(dt, tdtype, w, mode=0, o_pad=None):
     w = w.contiguous()
     O, I, R, S = w.shape
     o_pad = O if o_pad is None else o_pad
-    out = torch.empty((I, R * S, o_pad), device=w.device, dtype=tdtype)
+    out = torch.empty((planes(dt) * I, R * S, o_pad), device=w.device, dtype=tdtype)
     call("szn_pack_weight_dgrad", dt, ptr(w), ptr(out), O, I, R, S, o_pad, mode, _lib.stream())
     return out
 
@@ -134,6 +143,7 @@ class FCN32sFunction(torch.autograd.Function):
     def forward(ctx, module, x, *params):
         ctx.set_materialize_grads(False)  # an unused head (mode='fcn' / 'seenmask') arrives as None, not as zeros
         dt, tdtype = PRECISIONS[module.precision]
+        npl = planes(dt)
         st = _lib.stream()
         dev = x.device
         if x.dtype != torch.float32:
@@ -162,7 +172,7 @@ class FCN32sFunction(torch.autograd.Function):
         dims = {}   # name -> (H, W, C) of that activation
         # conv1_1 on CUDA cores straight from the NCHW image
         h, w_ = H + 198, W + 198
-        a = torch.empty((B, h, w_, 64), device=dev, dtype=tdtype)
+        a = torch.empty((B, h, w_, npl * 64), device=dev, dtype=tdtype)
         call("szn_conv1_1_fwd", dt, ptr(x), ptr(P["conv1_1.weight"].detach().contiguous()),
              ptr(P["conv1_1.bias"].detach()), ptr(a), B, H, W, 100, st)
         acts["conv1_1"], dims["conv1_1"] = a, (h, w_, 64)
@@ -171,12 +181,12 @@ class FCN32sFunction(torch.autograd.Function):
             name = row[0]
             if len(row) == 1:
                 ho, wo = (h + 1) // 2, (w_ + 1) // 2
-                o = torch.empty((B, ho, wo, c), device=dev, dtype=tdtype)
+                o = torch.empty((B, ho, wo, npl * c), device=dev, dtype=tdtype)
                 call("szn_pool_fwd", dt, ptr(a), ptr(o), B, h, w_, c, st)
                 h, w_ = ho, wo
             else:
                 _, cin, cout, k, pad = row
-                o = torch.empty((B, h, w_, cout), device=dev, dtype=tdtype)
+                o = torch.empty((B, h, w_, npl * cout), device=dev, dtype=tdtype)
                 call("szn_conv_fwd", dt, ptr(a), ptr(packed(name)), ptr(P[name + ".bias"].detach()), ptr(o),
                      B, h, w_, cin, cout, k, k, pad, 1, None, 0, 0, cout, st)
                 c = cout
@@ -195,10 +205,10 @@ class FCN32sFunction(torch.autograd.Function):
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
                 call("szn_dropout_scale", ptr(drop), 2 * B * 4096, seed, st)
         hs, ws = h - 6, w_ - 6
-        h6 = torch.empty((B, hs, ws, 4096), device=dev, dtype=tdtype)
+        h6 = torch.empty((B, hs, ws, npl * 4096), device=dev, dtype=tdtype)
         call("szn_conv_fwd", dt, ptr(a), ptr(packed("fc6")), ptr(P["fc6.bias"].detach()), ptr(h6), B, h, w_, 512, 4096,
              7, 7, 0, 1, ptr(drop[0]) if training else None, 4096, 0, 4096, st)
-        h7 = torch.empty((B, hs, ws, 4096), device=dev, dtype=tdtype)
+        h7 = torch.empty((B, hs, ws, npl * 4096), device=dev, dtype=tdtype)
         call("szn_conv_fwd", dt, ptr(h6), ptr(packed("fc7")), ptr(P["fc7.bias"].detach()), ptr(h7), B, hs, ws, 4096,
              4096, 1, 1, 0, 1, ptr(drop[1]) if training else None, 4096, 0, 4096, st)
         # score_fr and seenmask_score as ONE GEMM with N = D + 2 (padded to Dp)
@@ -245,6 +255,7 @@ class FCN32sFunction(torch.autograd.Function):
         sv = ctx.saved
         module = ctx.module
         dt, tdtype = sv["dt"], sv["tdtype"]
+        npl = planes(dt)
         st = _lib.stream()
         B, H, W, D, Dp, hs, ws = sv["geom"]
         P, acts, dims = sv["P"], sv["acts"], sv["dims"]
@@ -266,11 +277,11 @@ class FCN32sFunction(torch.autograd.Function):
         # ---------------- heads: d s17 ----------------
         if gf is None and gs is None and gs17 is None:
             return _finish(module, grads)
-        ds17 = zeros((B, hs, ws, Dp), tdtype)
+        ds17 = zeros((B, hs, ws, npl * Dp), tdtype)
         if gs17 is not None and gf is None:
             # fused head: d s17 arrives ready-made (fp32); store it in the trunk's gradient type (TF32-rounded / bf16).
             # Runs before the seen-mask head below, which overwrites its own two channels.
-            call("szn_cast", dt, ptr(gs17.contiguous().float()), ptr(ds17), ds17.numel(), st)
+            call("szn_cast", dt, ptr(gs17.contiguous().float()), ptr(ds17), B * hs * ws, Dp, st)
         if gf is not None:
             gf = gf.contiguous()
             if sv["diag"]:
@@ -284,8 +295,11 @@ class FCN32sFunction(torch.autograd.Function):
                 grads["upscore.weight"] = g
         if gs17 is not None and gf is not None:
             # the score was used both through the fused head and as a tensor: add the two contributions (rare)
-            both = ds17.float() + gs17.float()
-            call("szn_cast", dt, ptr(both), ptr(ds17), ds17.numel(), st)
+            prev = ds17.float()
+            if npl == 2:
+                prev = prev[..., :Dp] + prev[..., Dp:]  # hi + lo planes
+            both = (prev + gs17.float()).contiguous()
+            call("szn_cast", dt, ptr(both), ptr(ds17), B * hs * ws, Dp, st)
         if gs is not None:
             gs = gs.contiguous()
             call("szn_deconv_small_dgrad", dt, ptr(gs), ptr(P["seenmask_upscore.weight"].detach().contiguous()),
@@ -332,7 +346,7 @@ class FCN32sFunction(torch.autograd.Function):
             return fused_db[layer]
 
         drop = sv["drop"]
-        d7 = torch.empty((B, hs, ws, 4096), device=dev, dtype=tdtype)
+        d7 = torch.empty((B, hs, ws, npl * 4096), device=dev, dtype=tdtype)
         wf, ws_ = P["score_fr.weight"], P["seenmask_score.weight"]
         head_wd = pw.get(("head", "d", dt), (wf._version, ws_._version, wf.data_ptr()),
                          lambda: _pack_d(dt, tdtype, torch.cat([wf.detach(), ws_.detach()], 0).contiguous(), 0, Dp))
@@ -358,11 +372,11 @@ class FCN32sFunction(torch.autograd.Function):
                     grads[name + ".bias"] = db
             if not want_dx:
                 return None
-            dx = torch.empty((B, xh, xw, cin), device=dev, dtype=tdtype)
+            dx = torch.empty((B, xh, xw, npl * cin), device=dev, dtype=tdtype)
             if k >= 5 and pad == 0 and relu_ref is None and scale is None:
                 # fc6 (7x7 valid on 23x23): one GEMM against the (tap, ci)-major transposed weights gives per-tap
                 # columns, which szn_col2im folds back; 98 full N tiles instead of 49 taps x a 512-wide N
-                dcol = torch.empty((B, ho, wo, k * k * cin), device=dev, dtype=tdtype)
+                dcol = torch.empty((B, ho, wo, npl * k * k * cin), device=dev, dtype=tdtype)
                 call("szn_conv_dgrad", dt, ptr(dy), ptr(packed_d(name, 1)), ptr(dcol), B, ho, wo, k * k * cin, cout, 1, 1,
                      0, None, None, 0, cout, None, st)
                 call("szn_col2im", dt, ptr(dcol), ptr(dx), B, xh, xw, cin, k, k, st)
@@ -391,7 +405,7 @@ class FCN32sFunction(torch.autograd.Function):
                 # g = d(pool out); route to the pre-pool activation (the previous conv's ReLU output)
                 prev = rows[i - 1][0]
                 ph, pw_, pc = dims[prev]
-                dy = torch.empty((B, ph, pw_, pc), device=dev, dtype=tdtype)
+                dy = torch.empty((B, ph, pw_, npl * pc), device=dev, dtype=tdtype)
                 vec = 8 if tdtype == torch.bfloat16 else 4
                 fuse = 256 % (pc // vec) == 0
                 call("szn_pool_bwd", dt, ptr(acts[prev]), ptr(g), ptr(dy), B, ph, pw_, pc, 1,

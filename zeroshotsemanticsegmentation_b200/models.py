@@ -39,8 +39,13 @@ class FCN32s(nn.Module):
     (``seenmask_score``/``seenmask_upscore``), reference ``models.py:27-160``.
 
     Extra keyword arguments (not in the reference):
-      precision: ``"tf32"`` (fp32 storage, TF32 tensor-core products; meets the 1e-3 forward tolerance)
-                 or ``"bf16"`` (bf16 storage and products, fp32 accumulate).
+      precision: ``"fp32"`` -- fp32-grade: every stored value is a (hi, lo) pair of bf16 planes (the 4 bytes of an
+                 fp32) and every product is the error-compensated sum hi*hi + lo*hi + hi*lo of three bf16 tensor-core
+                 MMAs with fp32 accumulate (~2^-16 per product): forward AND gradients match the reference's fp32 CPU
+                 path to 1e-5 .. 1e-3 at every size, for 1.5x the tensor time of "tf32";
+                 ``"tf32"`` (default) -- fp32 storage rounded to TF32, TF32 products (2^-11 per operand): the
+                 throughput mode; forward within 1e-3 at the golden sizes, AT 1e-3 at 512x512 with O(1) activations;
+                 ``"bf16"`` -- bf16 storage and products, fp32 accumulate.
       upscore_weight_grad: also compute the dense ``upscore.weight.grad`` (213 GFLOP/image at D=300 for a
                  weight the reference never optimises, ``train.py:324-327``); off by default.
       fused_head: EXPERIMENTAL, off by default, not yet validated on a GPU.  The returned score carries a handle to the
