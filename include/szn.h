@@ -109,13 +109,15 @@ int szn_deconv_small_wgrad(const float* s, const float* g, float* dwd, int B, in
                            int ws, int ld, int coff, void* stream);
 
 /* ---- losses (utils.py:19-102).  score NCHW fp32, target int64 [n,h,w] with -1 = ignore.
- * kind 0 = cosine_loss (utils.py:75-102), 1 = mse_loss (utils.py:50-73).  accum = {sum, n_valid} (fp64, device). */
+ * kind 0 = cosine_loss (utils.py:75-102), 1 = mse_loss (utils.py:50-73).  accum = {sum, n_valid} (fp64, device).
+ * table [table_rows][c] (or null with an explicit target_embed): a label >= table_rows never reads past the table; it
+ * turns the loss into NaN (torch's embedding would device-assert), likewise a label >= c in szn_ce2d_*. */
 int szn_embed_loss_fwd(int kind, const float* score, const long long* target, const float* target_embed,
-                       const float* table, int n, int c, int h, int w, float* stats, double* accum, float* loss,
-                       void* stream);
+                       const float* table, int table_rows, int n, int c, int h, int w, float* stats, double* accum,
+                       float* loss, void* stream);
 int szn_embed_loss_bwd(int kind, const float* score, const long long* target, const float* target_embed,
-                       const float* table, int n, int c, int h, int w, const float* stats, const double* accum,
-                       const float* grad_out, float* dscore, void* stream);
+                       const float* table, int table_rows, int n, int c, int h, int w, const float* stats,
+                       const double* accum, const float* grad_out, float* dscore, void* stream);
 /* cross_entropy2d (utils.py:19-48) */
 int szn_ce2d_fwd(const float* score, const long long* target, int n, int c, int h, int w, int size_average, float* lse,
                  double* accum, float* loss, void* stream);

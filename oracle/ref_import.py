@@ -10,7 +10,9 @@ import os
 import sys
 import types
 
-REF_DIRS = ("/root/reference",)
+# the dev container's checkout, then a driver-installed copy inside the repo (git-ignored).  bench.py passes the
+# second one explicitly: nothing that runs on the GPU box may read /root/reference.
+REF_DIRS = ("/root/reference", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref"))
 
 
 def reference_root():
@@ -20,9 +22,9 @@ def reference_root():
     return None
 
 
-def load_reference():
-    root = reference_root()
-    if root is None:
+def load_reference(root=None):
+    root = root or reference_root()
+    if root is None or not os.path.isfile(os.path.join(root, "models.py")):
         raise FileNotFoundError("reference checkout not present")
     if "fcn" not in sys.modules:
         fcn = types.ModuleType("fcn")

@@ -13,11 +13,11 @@ import bench  # noqa: E402
 
 
 def test_algorithmic_flops_match_the_survey_table():
-    fwd, bwd = bench.trunk_flops_per_image(300)          # 380.01 GF forward, 758.28 GF backward per 512x512 image
+    fwd, bwd = bench.trunk_flops_per_image(300, 512)          # 380.01 GF forward, 758.28 GF backward per 512x512 image
     assert abs(fwd / 1e9 - 380.01) < 0.05 and abs(bwd / 1e9 - 758.28) < 0.1
-    fwd, bwd = bench.trunk_flops_per_image(1024)
+    fwd, bwd = bench.trunk_flops_per_image(1024, 512)
     assert abs(fwd / 1e9 - 381.72) < 0.05 and abs(bwd / 1e9 - 761.71) < 0.1
-    fwd, bwd = bench.trunk_flops_per_image(20)
+    fwd, bwd = bench.trunk_flops_per_image(20, 512)
     assert abs(fwd / 1e9 - 379.35) < 0.05 and abs(bwd / 1e9 - 756.95) < 0.1
 
 
@@ -37,6 +37,31 @@ def test_conv_flops_reads_the_abi_argument_positions():
     a = (0, 1, 2, 3, 4, 8, 23, 23, 512, 4096, 7, 7, 0, 1, None, 0, 0, 4096, 0)
     assert bench.conv_flops("szn_conv_fwd", a) == 2.0 * 8 * 17 * 17 * 4096 * 49 * 512
     assert bench.conv_flops("szn_pool_fwd", a) == 0
+
+
+def test_hbm_bytes_reads_the_abi_argument_positions():
+    """hbm_bytes: algorithmic bytes of the HBM-bound kernels from their C-ABI argument tuples (include/szn.h)."""
+    B, D, H = 8, 300, 512
+    # szn_embed_loss_fwd(kind, score, target, target_embed, table, table_rows, n, c, h, w, stats, accum, loss, stream)
+    a = (0, 1, 2, None, 4, 59, B, D, H, H, 5, 6, 7, 0)
+    assert bench.hbm_bytes("szn_embed_loss_fwd", a, 4) == B * H * H * (D * 4 + 8)
+    # szn_embed_argmax(score, table, n, D, h, w, C, scratch, labels, stream)
+    assert bench.hbm_bytes("szn_embed_argmax", (1, 2, B, D, H, H, 59, 3, 4, 0), 4) == B * H * H * (D * 4 + 8)
+    # szn_upsample32_crop_fwd(s, out, B, D, H, W, hs, ws, ld, coff, stream) / _bwd(dtype, g, ds, B, D, H, W, ...)
+    assert bench.hbm_bytes("szn_upsample32_crop_fwd", (1, 2, B, D, H, H, 17, 17, 320, 0, 0), 4) == B * D * H * H * 4
+    assert bench.hbm_bytes("szn_upsample32_crop_bwd", (0, 1, 2, B, D, H, H, 17, 17, 320, 0, 0), 4) == B * D * H * H * 4
+    # szn_conv1_1_fwd(dtype, x, w, bias, y, B, H, W, pad, stream): image in, 710 x 710 x 64 out
+    assert bench.hbm_bytes("szn_conv1_1_fwd", (0, 1, 2, 3, 4, B, H, H, 100, 0), 4) == B * 3 * H * H * 4 + B * 710 * 710 * 64 * 4
+    # szn_pool_bwd(dtype, y, dp, dy, B, H, W, C, relu_gate, col_sum, stream)
+    assert bench.hbm_bytes("szn_pool_bwd", (1, 1, 2, 3, B, 710, 710, 64, 1, None, 0), 2) == B * 710 * 710 * 64 * 2 * 2.25
+    assert bench.hbm_bytes("szn_conv_fwd", a, 4) == 0
+
+
+def test_every_baseline_config_is_selectable():
+    assert sorted(bench.CONFIGS) == [0, 1, 2, 3, 4]
+    assert bench.CONFIGS[1]["B"] == 8 and bench.CONFIGS[1]["precision"] == "tf32" and bench.CONFIGS[2]["B"] == 32
+    assert bench.CONFIGS[3].get("zeroshot") and bench.CONFIGS[4]["D"] == 1024 and bench.CONFIGS[4]["C"] == 256
+    assert len(bench.VAL_UNSEEN) == 10 and set(bench.VAL_UNSEEN).isdisjoint(bench.TRAIN_UNSEEN)
 
 
 def test_clock_sample_parser(tmp_path):

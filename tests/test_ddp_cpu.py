@@ -22,6 +22,12 @@ class _FakeModel:
     _grad_ready = None
     _grad_flush = None
 
+    def parameters(self):
+        return []
+
+    def buffers(self):
+        return []
+
 
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -50,6 +56,48 @@ def _worker(rank, world, port, out):
     ok = ok and red.bytes_reduced == sum(t.numel() * 4 for t in local)
     out[rank] = bool(ok)
     dist.destroy_process_group()
+
+
+def _bcast_worker(rank, world, port, out):
+    """Replicas start from rank 0's weights (score_fr / seenmask_score keep a per-process random init), also
+    for channels_last parameters; validation histograms are summed over the ranks; only rank 0 is the writer."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from zeroshotsemanticsegmentation_b200 import ddp
+    torch.manual_seed(100 + rank)  # every rank draws other initial weights
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(8, 4, 3)
+            self.conv.weight.data = self.conv.weight.data.contiguous(memory_format=torch.channels_last)
+            self.fc = torch.nn.Linear(5, 3)
+            self.register_buffer("filt", torch.randn(4, 4))
+            self._grad_ready = self._grad_flush = None
+
+    m = M()
+    before = [p.detach().clone() for p in m.parameters()]
+    red = ddp.GradientAllReduce(m)
+    state = [t.detach().contiguous().clone() for t in list(m.parameters()) + list(m.buffers())]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, state)
+    same = all(torch.equal(a, b) for a, b in zip(gathered[0], gathered[1]))
+    kept_layout = m.conv.weight.permute(0, 2, 3, 1).is_contiguous()
+    rank0_untouched = rank != 0 or all(torch.equal(a, b) for a, b in zip(before, m.parameters()))
+    hist = torch.full((3, 3), float(rank + 1))
+    red.all_reduce_hist(hist)
+    out[rank] = bool(same and kept_layout and rank0_untouched and torch.equal(hist, torch.full((3, 3), 3.0))
+                     and red.is_main == (rank == 0))
+    dist.destroy_process_group()
+
+
+def test_parameters_are_broadcast_and_hists_reduced_world2_gloo():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_bcast_worker, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
 
 
 def test_gradient_allreduce_world2_gloo():

@@ -114,3 +114,74 @@ def test_non_contiguous_scores_and_explicit_target_embed():
         assert abs(U.cosine_loss(sd, lab.to(DEV), te.to(DEV)).item() - want) < 1e-5
         assert abs(U.cosine_loss(sd, lab.to(DEV), table=tab.to(DEV)).item() - want) < 1e-5
         assert (U.infer_lbl(sd, tab.to(DEV)) == O.infer_lbl(score.contiguous(), tab)).mean() > 0.99
+
+
+def test_out_of_range_labels_poison_the_loss_instead_of_reading_out_of_bounds():
+    """a label >= the table's rows (an un-remapped 255, a 59- vs 33-class table) or >= the CE channel count used
+    to index past the table / score and return a plausible finite number.  torch's embedding / nll_loss device-assert on
+    such input; here the loss is NaN (the trainers' NaN guard, trainer_fcn.py:107-108, raises) and backward stays in
+    bounds."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    g = torch.Generator().manual_seed(4)
+    score = torch.randn(2, 6, 8, 12, generator=g).to(DEV).requires_grad_(True)
+    tab = torch.randn(5, 6, generator=g).to(DEV)
+    lab = torch.randint(0, 5, (2, 8, 12), generator=g)
+    ok = U.cosine_loss(score, lab.to(DEV), table=tab)
+    assert math.isfinite(ok.item())
+    bad = lab.clone()
+    bad[1, 3, 4] = 5      # == rows
+    bad[0, 0, 0] = 255    # the raw VOC ignore label, not remapped to -1
+    for fn in (U.cosine_loss, U.mse_loss):
+        loss = fn(score, bad.to(DEV), table=tab)
+        assert math.isnan(loss.item())
+        loss.backward()   # must not fault
+        torch.cuda.synchronize()
+    ce_score = torch.randn(2, 5, 8, 12, generator=g).to(DEV).requires_grad_(True)
+    assert math.isfinite(U.cross_entropy2d(ce_score, lab.to(DEV)).item())
+    loss = U.cross_entropy2d(ce_score, bad.to(DEV), size_average=True)
+    assert math.isnan(loss.item())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert (ce_score.grad[0, :, 0, 0] == 0).all() and (ce_score.grad[1, :, 3, 4] == 0).all()
+
+
+def test_data_edits_need_invalidate_and_padded_seenmask_batches_ignore_the_padding():
+    """(1) parameters edited through .data do not advance the version counter the packed-weight cache keys on:
+    invalidate_weight_cache() (also called by load_state_dict / .to() / copy_params_from_vgg16) makes them visible.
+    (2) a ragged B=2 seen-mask batch: padded pixels neither enter the mean CE nor get a gradient."""
+    import zeroshotsemanticsegmentation_b200 as szn
+    from zeroshotsemanticsegmentation_b200 import trainer as T
+    U = szn.utils
+    D, C = 5, 7
+    params = O.init_params(D, seed=3)
+    m = szn.FCN32s(D)
+    m.load_state_dict(params)
+    m = m.to(DEV).eval()
+    x, lab, tab = O.synth_batch(1, 24, 31, C, D, seed=9, block=4)
+    with torch.no_grad():
+        f0 = m(x.to(DEV)).clone()
+        m.conv3_2.weight.data.mul_(1.5)      # version counter unchanged: the cached pack is still used
+        m.invalidate_weight_cache()
+        f1 = m(x.to(DEV)).clone()
+    p2 = {k: v.clone() for k, v in params.items()}
+    p2["conv3_2.weight"] = p2["conv3_2.weight"] * 1.5
+    assert rel(f1.cpu().numpy(), O.forward(x, p2, "fcn").numpy()) < 1e-3 and not torch.equal(f0, f1)
+    # ragged seen-mask batch
+    a = O.synth_batch(1, 24, 31, C, D, seed=10, block=4)
+    b = O.synth_batch(1, 17, 20, C, D, seed=11, block=4)
+    data, target = T.collate_padded([(a[0][0], a[1][0]), (b[0][0], b[1][0])])
+    unseen = [1, 4]
+    t = U.seenmask_target(target.to(DEV), unseen, C)
+    s = m(data.to(DEV), mode="seenmask")
+    s.retain_grad()
+    loss = U.cross_entropy2d(s, t, size_average=True)
+    loss.backward()
+    # oracle: the same scores, per item on its own unpadded window, normalised by the total valid count
+    so = s.detach().cpu()
+    tot, cnt = 0.0, 0
+    for i, (h, w, item) in enumerate(((24, 31, a), (17, 20, b))):
+        ti = O.seenmask_target(item[1], unseen, C)
+        tot += O.cross_entropy2d(so[i:i + 1, :, :h, :w], ti, size_average=False).item()
+        cnt += int((ti >= 0).sum())
+    assert abs(loss.item() - tot / cnt) < 1e-5 * max(1.0, abs(tot / cnt))
+    assert (s.grad[1, :, 17:, :] == 0).all() and (s.grad[1, :, :, 20:] == 0).all() and s.grad[1, :, :17, :20].abs().sum() > 0

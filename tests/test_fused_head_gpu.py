@@ -1,16 +1,13 @@
-"""EXPERIMENTAL fused head (FCN32s(fused_head=True), szn_head_fused_*): loss, labels and d s17 from the 17x17 score map
-against the ordinary path that materialises the (B, D, H, W) score.  Written without GPU access at the end of round 1:
-run with SZN_EXPERIMENTAL=1 (the default `pytest -m gpu` run skips it until it has been seen green on a B200)."""
-import os
-
+"""Fused head (FCN32s(fused_head=True), szn_head_fused_*): loss, labels and d s17 from the 17x17 score map against the
+ordinary path that materialises the (B, D, H, W) score (the parity reference; SURVEY 7 "commuting the head").  Green on a
+B200 since the first GPU call of round 2."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import szn_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SZN_EXPERIMENTAL") != "1", reason="experimental: set SZN_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 

@@ -27,9 +27,25 @@ def test_collate_pads_images_with_zero_and_labels_with_ignore():
         assert torch.equal(data[b, :, :h, :w], img) and torch.equal(target[b, :h, :w], lbl)
         pad = torch.ones(40, 64, dtype=torch.bool)
         pad[:h, :w] = False
-        assert (target[b][pad] == -1).all() and (data[b][:, pad] == 0).all()
+        assert (target[b][pad] == T.PAD_LABEL).all() and (data[b][:, pad] == 0).all()
     # the number of valid pixels (what every loss and metric normalises by) is unchanged by padding
     assert int((target >= 0).sum()) == sum(int((l >= 0).sum()) for _, l in its)
+
+
+def test_padding_stays_ignored_in_the_seenmask_target():
+    """the seen-mask target maps the dataset's ignore label -1 to class 0 (upstream, trainer_seenmask.py:55-56)
+    but must NOT do that to the padding collate_padded adds for B > 1, or pad regions would be trained as 'unseen'."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    a = (torch.ones(3, 4, 6), torch.tensor([[0, 1, 2, -1, 3, 4]] * 4))
+    b = (torch.ones(3, 2, 3), torch.tensor([[5, -1, 2]] * 2))
+    data, target = T.collate_padded([a, b])
+    assert target.shape == (2, 4, 6) and T.PAD_LABEL < -1
+    assert (target[1, 2:, :] == T.PAD_LABEL).all() and (target[1, :2, 3:] == T.PAD_LABEL).all()
+    t = U.seenmask_target(target, unseen=[2, 5], n_class=6)
+    assert t[0].tolist() == [[1, 1, 0, 0, 1, 1]] * 4                      # -1 -> 0 like upstream, unseen 2 -> 0
+    assert t[1, :2, :3].tolist() == [[0, 0, 0]] * 2                        # 5 unseen, -1 -> 0, 2 unseen
+    assert (t[1, 2:, :] < 0).all() and (t[1, :2, 3:] < 0).all()           # padding stays ignored
+    assert (t >= 0).sum().item() == 24 + 6
 
 
 def test_collate_single_item_is_the_reference_batch():

@@ -33,8 +33,8 @@ SIGNATURES = {
     "szn_deconv_small_fwd": [P, P, P, I, I, I, I, I, I, I, I, I, P],
     "szn_deconv_small_dgrad": [I, P, P, P, I, I, I, I, I, I, I, I, I, P],
     "szn_deconv_small_wgrad": [P, P, P, I, I, I, I, I, I, I, I, I, P],
-    "szn_embed_loss_fwd": [I, P, P, P, P, I, I, I, I, P, P, P, P],
-    "szn_embed_loss_bwd": [I, P, P, P, P, I, I, I, I, P, P, P, P, P],
+    "szn_embed_loss_fwd": [I, P, P, P, P, I, I, I, I, I, P, P, P, P],
+    "szn_embed_loss_bwd": [I, P, P, P, P, I, I, I, I, I, P, P, P, P, P],
     "szn_ce2d_fwd": [P, P, I, I, I, I, I, P, P, P, P],
     "szn_ce2d_bwd": [P, P, I, I, I, I, I, P, P, P, P, P],
     "szn_loss_finalize": [I, P, P, P],

@@ -291,8 +291,11 @@ __device__ __forceinline__ void block_accumulate(double a, double b, double* acc
 template <int KIND, int VEC, bool HAS_TE>
 __global__ void __launch_bounds__(256, 3) embed_loss_fwd_kernel(const float* __restrict__ score, const long long* __restrict__ target,
                                                              const float* __restrict__ te, const float* __restrict__ table,
-                                                             int n, int c, long long hw, float* __restrict__ stats,
+                                                             int n, int c, long long hw, int rows, float* __restrict__ stats,
                                                              double* __restrict__ accum) {
+  // rows = rows of `table`: a label >= rows (an un-remapped 255, a table of another dataset) must not index past it.
+  // torch's embedding / nll_loss device-assert on such input; here the pixel reads row rows-1 and poisons the loss with
+  // NaN, which the trainers' NaN guard (trainer_fcn.py:107-108) turns into an exception.
   const long long total = n * hw / VEC;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   double part = 0, cnt = 0;
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(256, 3) embed_loss_fwd_kernel(const float* __r
       const float* ep = HAS_TE ? te + b * c * hw + p : nullptr;
       const float* tp[VEC];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) tp[j] = HAS_TE ? nullptr : table + (t[j] >= 0 ? t[j] : 0) * c;
+      for (int j = 0; j < VEC; ++j) tp[j] = HAS_TE ? nullptr : table + (t[j] < 0 ? 0 : t[j] < rows ? t[j] : rows - 1) * c;
       float ss[VEC], se[VEC], ee[VEC], sq[VEC];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) ss[j] = se[j] = ee[j] = sq[j] = 0.f;
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(256, 3) embed_loss_fwd_kernel(const float* __r
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         if (t[j] < 0) continue;
+        if (!HAS_TE && t[j] >= rows) part += (double)NAN;  // out-of-range label
         if (KIND == 0) {
           const float inv_s = 1.f / sqrtf(ss[j]), inv_e = 1.f / sqrtf(ee[j]);
           const float cs = se[j] * inv_s * inv_e;
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(256, 3) embed_loss_fwd_kernel(const float* __r
 template <int KIND, int VEC, bool HAS_TE>
 __global__ void __launch_bounds__(256, 2) embed_loss_bwd_kernel(const float* __restrict__ score, const long long* __restrict__ target,
                                                              const float* __restrict__ te, const float* __restrict__ table,
-                                                             int n, int c, long long hw, const float* __restrict__ stats,
+                                                             int n, int c, long long hw, int rows, const float* __restrict__ stats,
                                                              const double* __restrict__ accum, const float* __restrict__ gout,
                                                              float* __restrict__ dscore) {
   const long long total = n * hw / VEC;
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(256, 2) embed_loss_bwd_kernel(const float* __r
   float inv_s[VEC], inv_e[VEC], cs[VEC], live[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
-    tp[j] = HAS_TE ? nullptr : table + (t[j] >= 0 ? t[j] : 0) * c;
+    tp[j] = HAS_TE ? nullptr : table + (t[j] < 0 ? 0 : t[j] < rows ? t[j] : rows - 1) * c;
     live[j] = t[j] >= 0 ? 1.f : 0.f;
     inv_s[j] = inv_e[j] = cs[j] = 0.f;
     if (KIND == 0 && t[j] >= 0) {
@@ -441,7 +445,9 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ s
     for (int d = 0; d < c; ++d) se += expf(sp[d * hw] - m);
     const float lse = m + logf(se);
     lse_out[i] = lse;
-    if (t >= 0) {
+    if (t >= c) {
+      part = (double)NAN, cnt = 1;  // out-of-range label: poison the loss instead of reading past the score (see above)
+    } else if (t >= 0) {
       part = (double)(lse - sp[t * hw]);
       cnt = 1;
     }
@@ -460,7 +466,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ s
   const long long b = i / hw, p = i - b * hw;
   const float* sp = score + b * c * hw + p;
   float* gp = dscore + b * c * hw + p;
-  if (t < 0) {
+  if (t < 0 || t >= c) {
     for (int d = 0; d < c; ++d) gp[d * hw] = 0.f;
     return;
   }
@@ -677,17 +683,18 @@ extern "C" int szn_deconv_small_wgrad(const float* s, const float* g, float* dwd
 // kind: 0 cosine, 1 mse.  Exactly one of target_embed ([n,c,h,w]) / table ([C,c], row = label, -1 ignored) is given.
 // stats: [n*h*w*3] fp32 scratch kept for backward (cosine); accum: 2 doubles {sum, n_valid}; loss: 1 float.
 extern "C" int szn_embed_loss_fwd(int kind, const float* score, const long long* target, const float* target_embed,
-                                  const float* table, int n, int c, int h, int w, float* stats, double* accum,
-                                  float* loss, void* stream) {
+                                  const float* table, int table_rows, int n, int c, int h, int w, float* stats,
+                                  double* accum, float* loss, void* stream) {
   if ((target_embed == nullptr) == (table == nullptr))
     return set_error(SZN_ERR_ARG, "szn_embed_loss_fwd: give exactly one of target_embed / table");
+  if (table && table_rows < 1) return set_error(SZN_ERR_ARG, "szn_embed_loss_fwd: table_rows must be the number of table rows");
   cudaStream_t st = (cudaStream_t)stream;
   const long long hw = (long long)h * w, total = n * hw;
   cudaMemsetAsync(accum, 0, 2 * sizeof(double), st);
   if (kind != 0 && kind != 1) return set_error(SZN_ERR_ARG, "szn_embed_loss_fwd: kind");
   const bool v4 = hw % 4 == 0 && ((reinterpret_cast<uintptr_t>(score) | reinterpret_cast<uintptr_t>(target_embed)) & 15) == 0;
   const unsigned grid = (unsigned)((total / (v4 ? 4 : 1) + 255) / 256);
-#define SZN_LOSS_FWD(K, V, TE) embed_loss_fwd_kernel<K, V, TE><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum)
+#define SZN_LOSS_FWD(K, V, TE) embed_loss_fwd_kernel<K, V, TE><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, table_rows, stats, accum)
   const bool has_te = target_embed != nullptr;
   if (kind == 0 && v4) { if (has_te) SZN_LOSS_FWD(0, 4, true); else SZN_LOSS_FWD(0, 4, false); }
   else if (kind == 0) { if (has_te) SZN_LOSS_FWD(0, 1, true); else SZN_LOSS_FWD(0, 1, false); }
@@ -705,7 +712,7 @@ extern "C" int szn_loss_finalize(int kind, const double* accum, float* loss, voi
 }
 
 extern "C" int szn_embed_loss_bwd(int kind, const float* score, const long long* target, const float* target_embed,
-                                  const float* table, int n, int c, int h, int w, const float* stats,
+                                  const float* table, int table_rows, int n, int c, int h, int w, const float* stats,
                                   const double* accum, const float* grad_out, float* dscore, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const long long hw = (long long)h * w, total = n * hw;
@@ -713,7 +720,7 @@ extern "C" int szn_embed_loss_bwd(int kind, const float* score, const long long*
   const bool v4 = hw % 4 == 0 && ((reinterpret_cast<uintptr_t>(score) | reinterpret_cast<uintptr_t>(target_embed) |
                                    reinterpret_cast<uintptr_t>(dscore)) & 15) == 0;
   const unsigned grid = (unsigned)((total / (v4 ? 4 : 1) + 255) / 256);
-#define SZN_LOSS_BWD(K, V, TE) embed_loss_bwd_kernel<K, V, TE><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, stats, accum, grad_out, dscore)
+#define SZN_LOSS_BWD(K, V, TE) embed_loss_bwd_kernel<K, V, TE><<<grid, 256, 0, st>>>(score, target, target_embed, table, n, c, hw, table_rows, stats, accum, grad_out, dscore)
   const bool has_te = target_embed != nullptr;
   if (kind == 0 && v4) { if (has_te) SZN_LOSS_BWD(0, 4, true); else SZN_LOSS_BWD(0, 4, false); }
   else if (kind == 0) { if (has_te) SZN_LOSS_BWD(0, 1, true); else SZN_LOSS_BWD(0, 1, false); }

@@ -17,7 +17,7 @@ import torch.distributed as dist
 class GradientAllReduce:
     """Attach to an ``FCN32s``: ``GradientAllReduce(model).accum_hook`` goes to the loss functions."""
 
-    def __init__(self, model, group=None, small_bytes=1 << 20):
+    def __init__(self, model, group=None, small_bytes=1 << 20, sync_params=True):
         self.model = model
         self.group = group
         self.small_bytes = small_bytes
@@ -25,9 +25,46 @@ class GradientAllReduce:
         self.small = []
         self.bytes_reduced = 0
         self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.rank = dist.get_rank(group) if self.enabled else 0
         if self.enabled:
             model._grad_ready = self._on_ready
             model._grad_flush = self._flush
+            if sync_params:
+                self.broadcast_parameters()
+
+    def broadcast_parameters(self, src=0):
+        """Replicas must start from the same weights: score_fr / seenmask_score keep torch's random default init
+        (models.py:104-108), which differs per process unless every rank seeds identically.  Rank ``src``'s parameters and
+        buffers are broadcast in place (channels_last parameters through their dense storage order)."""
+        if not self.enabled:
+            return
+        with torch.no_grad():
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                if t.is_contiguous():
+                    dist.broadcast(t, src=src, group=self.group)
+                elif t.dim() == 4 and t.permute(0, 2, 3, 1).is_contiguous():
+                    dist.broadcast(t.permute(0, 2, 3, 1), src=src, group=self.group)
+                else:
+                    tmp = t.contiguous()
+                    dist.broadcast(tmp, src=src, group=self.group)
+                    t.copy_(tmp)
+        if hasattr(self.model, "_packed"):
+            self.model._packed.invalidate()  # in-place writes under no_grad do bump versions; be explicit anyway
+
+    def all_reduce_hist(self, hist):
+        """Sum a device confusion histogram over the ranks (validation metrics must not be rank-local)."""
+        if self.enabled:
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
+        return hist
+
+    @property
+    def is_main(self):
+        """True on the one rank that may write logs / checkpoints."""
+        return self.rank == 0
+
+    def barrier(self):
+        if self.enabled:
+            dist.barrier(group=self.group)
 
     def _on_ready(self, name, g):
         nbytes = g.numel() * g.element_size()

@@ -53,10 +53,16 @@ def round_up(a, b):
 
 
 class PackedWeights:
-    """Per-module cache of kernel-layout weights, refreshed when a parameter's version changes."""
+    """Per-module cache of kernel-layout weights, refreshed when a parameter's version changes.  Edits through ``.data``
+    (``p.data.copy_()``, the style the reference's own init / copy code uses) do NOT advance the version counter: call
+    ``invalidate()`` after them -- ``FCN32s`` does so itself in ``copy_params_from_vgg16``, ``load_state_dict`` and
+    ``_apply`` (``.to()`` / ``.cuda()`` / ``.float()``)."""
 
     def __init__(self):
         self.cache = {}
+
+    def invalidate(self):
+        self.cache.clear()
 
     def get(self, key, version, build):
         hit = self.cache.get(key)
@@ -222,7 +228,9 @@ class FCN32sFunction(torch.autograd.Function):
             return _pack(dt, tdtype, cat, Dp), bias
 
         head_w, head_b = pw.get(("head", dt), (wf._version, ws_._version, P["score_fr.bias"]._version,
-                                                P["seenmask_score.bias"]._version, wf.data_ptr()), build_head)
+                                                P["seenmask_score.bias"]._version, wf.data_ptr(), ws_.data_ptr(),
+                                                P["score_fr.bias"].data_ptr(), P["seenmask_score.bias"].data_ptr()),
+                                  build_head)
         s17 = torch.empty((B, hs, ws, Dp), device=dev, dtype=torch.float32)
         call("szn_conv_fwd", dt, ptr(h7), ptr(head_w), ptr(head_b), ptr(s17), B, hs, ws, 4096, Dp, 1, 1, 0, 0,
              None, 0, 1, Dp, st)
@@ -348,7 +356,7 @@ class FCN32sFunction(torch.autograd.Function):
         drop = sv["drop"]
         d7 = torch.empty((B, hs, ws, npl * 4096), device=dev, dtype=tdtype)
         wf, ws_ = P["score_fr.weight"], P["seenmask_score.weight"]
-        head_wd = pw.get(("head", "d", dt), (wf._version, ws_._version, wf.data_ptr()),
+        head_wd = pw.get(("head", "d", dt), (wf._version, ws_._version, wf.data_ptr(), ws_.data_ptr()),
                          lambda: _pack_d(dt, tdtype, torch.cat([wf.detach(), ws_.detach()], 0).contiguous(), 0, Dp))
         call("szn_conv_dgrad", dt, ptr(ds17), ptr(head_wd), ptr(d7), B, hs, ws, 4096, Dp, 1, 1, 0,
              ptr(sv["h7"]), ptr(drop[1]) if drop is not None else None, 4096, Dp, ptr(db_buffer("fc7")), st)

@@ -48,11 +48,14 @@ class FCN32s(nn.Module):
                  ``"bf16"`` -- bf16 storage and products, fp32 accumulate.
       upscore_weight_grad: also compute the dense ``upscore.weight.grad`` (213 GFLOP/image at D=300 for a
                  weight the reference never optimises, ``train.py:324-327``); off by default.
-      fused_head: EXPERIMENTAL, off by default, not yet validated on a GPU.  The returned score carries a handle to the
-                 17x17 score map it was upsampled from; ``utils.cosine_loss(score, target, table=E)`` and
-                 ``utils.infer_lbl*`` then work from that map (``szn_head_fused_*``) instead of making four passes over
-                 the (B, D, H, W) tensor, and the loss gradient re-enters the network as d s17.  Any other use of the
-                 score (or an in-place change of it) silently takes the ordinary path.
+      fused_head: the returned score carries a handle to the 17x17 score map it was upsampled from;
+                 ``utils.cosine_loss / mse_loss(score, target, table=E)`` and ``utils.infer_lbl*`` then work from that
+                 map (``szn_head_fused_*``: the x32 upsample is linear and per channel, so per-pixel dot products and
+                 norms follow from a 289 x C product and a neighbour Gram matrix) instead of making four passes over the
+                 (B, D, H, W) tensor, and the loss gradient re-enters the network as d s17.  Any other use of the score
+                 (or an in-place change of it) silently takes the ordinary path.  Loss and gradients agree with the
+                 ordinary path to fp32 rounding; labels differ only at near-ties (another summation order), so the
+                 ordinary path stays the default and the parity reference.
     """
 
     def __init__(self, n_class=21, precision="tf32", upscore_weight_grad=False, fused_head=False):
@@ -102,6 +105,22 @@ class FCN32s(nn.Module):
             if isinstance(m, nn.Conv2d) and m.kernel_size[0] > 1 and m.in_channels > 3:
                 m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
 
+    def invalidate_weight_cache(self):
+        """Forget the packed (kernel-layout) copies of the weights.  Needed after editing parameters through ``.data``
+        (``p.data.copy_()`` / ``mul_()`` / ``clamp_()``), which does not advance the version counters the cache keys on."""
+        self._packed.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "_packed"):
+            self._packed.invalidate()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._packed.invalidate()
+        return out
+
     def _ordered_params(self):
         sd = dict(self.named_parameters())
         return [sd[n] for n in engine.PARAM_ORDER]
@@ -134,3 +153,4 @@ class FCN32s(nn.Module):
             dst.weight.data = src.weight.data.view(dst.weight.size())
             dst.bias.data = src.bias.data.view(dst.bias.size())
         self._use_kernel_weight_layout()  # the copied tensors are NCHW-dense: back to the layout the wgrad kernel writes
+        self._packed.invalidate()         # `.data =` swaps storage without touching the version counters

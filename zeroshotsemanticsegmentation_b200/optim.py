@@ -115,7 +115,15 @@ def _bump_versions(params):
         return
     setter = getattr(torch._C._autograd, "_unsafe_set_version_counter", None)
     if setter is not None:
-        setter(tuple(params), tuple(p._version + 1 for p in params))
-    else:  # older torch: an in-place no-op does the same at the price of one more pass
-        for p in params:
-            p.add_(0.0)
+        try:
+            setter(tuple(params), tuple(p._version + 1 for p in params))
+            return
+        except TypeError:  # torch 2.x before the tuple overload: the signature is (Tensor, int)
+            try:
+                for p in params:
+                    setter(p, p._version + 1)
+                return
+            except TypeError:
+                pass
+    for p in params:  # no usable setter: an in-place no-op does the same at the price of one more pass
+        p.add_(0.0)

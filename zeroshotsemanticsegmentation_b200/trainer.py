@@ -42,13 +42,18 @@ VAL_HEADERS = ["epoch", "iteration", "val/loss", "val/pxl_acc", "val/class_acc",
 EARLY_STOP_ITERS = {"pascal": 425000, "context": 247000}
 
 
+PAD_LABEL = -2  # label of pixels added by collate_padded: ignored like -1 everywhere, but never re-mapped (see below)
+
+
 def collate_padded(samples, multiple=1, size=None):
     """``collate_fn`` for ``DataLoader(batch_size > 1)`` over the reference datasets (``pascal_dataset.py:106-133``,
     ``context_dataset.py:116-138``): items are ``(img (3,h,w) fp32, lbl (h,w) int64)`` or ``(img, (lbl, lbl_vec))``;
     ``lbl_vec`` is dropped (the fused loss gathers it from the table).  Images are padded bottom/right with 0, labels
-    with -1, to the batch maximum rounded up to ``multiple`` (or to ``size=(H, W)``).  Returns ``(data (B,3,H,W),
-    target (B,H,W))``.  Padded pixels are ignored by every loss and metric (``target >= 0`` masks, ``utils.py:36,60,85,
-    106``); with B == 1 and no rounding the item is returned untouched, i.e. exactly the reference's batch."""
+    with ``PAD_LABEL`` (-2), to the batch maximum rounded up to ``multiple`` (or to ``size=(H, W)``).  Returns ``(data
+    (B,3,H,W), target (B,H,W))``.  Padded pixels are ignored by every loss and metric (``target >= 0`` masks,
+    ``utils.py:36,60,85,106``) -- also in the seen-mask phase, whose target maps the dataset's ignore label -1 to class 0
+    like upstream (``trainer_seenmask.py:55-56``) but leaves the padding negative; with B == 1 and no rounding the item is
+    returned untouched, i.e. exactly the reference's batch."""
     imgs, lbls = [], []
     for img, tgt in samples:
         lbl = tgt[0] if isinstance(tgt, (tuple, list)) else tgt
@@ -66,7 +71,7 @@ def collate_padded(samples, multiple=1, size=None):
         W = max(i.shape[2] for i in imgs)
         H, W = -(-H // multiple) * multiple, -(-W // multiple) * multiple
     data = torch.zeros((len(imgs), imgs[0].shape[0], H, W), dtype=torch.float32)
-    target = torch.full((len(imgs), H, W), -1, dtype=torch.int64)
+    target = torch.full((len(imgs), H, W), PAD_LABEL, dtype=torch.int64)
     for b, (img, lbl) in enumerate(zip(imgs, lbls)):
         h, w = lbl.shape
         if h > H or w > W:
@@ -133,8 +138,19 @@ class _Base(object):
         # the valid-pixel count of the GLOBAL batch; gradients are all-reduced inside backward
         self.reducer = reducer
         self._accum_hook = reducer.accum_hook if reducer is not None else None
+        # rank awareness: validation histograms are summed over the ranks (each rank sees its shard of the loader), and only
+        # the main rank writes CSV logs, tensorboard scalars and checkpoints (all ranks would otherwise race on one log_dir)
+        self.is_main = getattr(reducer, "is_main", True)
+        if not self.is_main:
+            self.log_dir = log_dir = None
+            self.tb_writer = None
+            self.verbose = False
         if log_dir:
             os.makedirs(log_dir, exist_ok=True)
+
+    def _global_hist(self, hist):
+        fn = getattr(self.reducer, "all_reduce_hist", None)
+        return fn(hist) if fn is not None else hist
 
     # ---- logging (same files and columns as the reference) ----
     def _init_log(self, name, headers):
@@ -315,7 +331,7 @@ class Trainer(_Base):
                     self.visualize(data, lbl_true, lbl_pred)
         if hist is None:
             raise ValueError("empty validation loader")
-        res = utils.metrics_from_hist(hist)
+        res = utils.metrics_from_hist(self._global_hist(hist))
         val_loss /= batches  # averaged over the batches of the loader (trainer_fcn.py:248)
         if self.unseen:
             metrics, seen_metrics, unseen_metrics = res
@@ -393,7 +409,7 @@ class SeenmaskTrainer(_Base):
                     self.visualize(data, lbl_true, lbl_pred)
         if hist is None:
             raise ValueError("empty validation loader")
-        metrics = utils.metrics_from_hist(hist)[0]
+        metrics = utils.metrics_from_hist(self._global_hist(hist))[0]
         val_loss /= batches
         self._append_log("seenmask_val_log.csv", [self.epoch, self.iteration, val_loss] + list(metrics) + [self._elapsed()])
         self._scalars("val", [val_loss] + list(metrics), self.epoch)

@@ -49,12 +49,13 @@ def split_embeddings(embed_arr, unseen):
 
 def seenmask_target(target, unseen, n_class):
     """Binary target of the seen-mask phase (``trainer_seenmask.py:53-56``): 1 where the label is a seen class, else 0
-    (the ignore label -1 therefore becomes 0 and is NOT ignored, as upstream).  Works on the tensor's own device, so the
-    label map need not visit the host."""
+    (the ignore label -1 therefore becomes 0 and is NOT ignored, as upstream).  Labels below -1 are batch padding
+    (``trainer.collate_padded``), which upstream never has: they stay negative, so the loss and the metrics skip them.
+    Works on the tensor's own device, so the label map need not visit the host."""
     unseen = torch.as_tensor(sorted(set(int(u) for u in unseen)), dtype=torch.long, device=target.device)
     t = target.long()
     seen = (t >= 0) & (t < n_class) & ~torch.isin(t, unseen)
-    return seen.long()
+    return torch.where(t < -1, t, seen.long())
 
 
 def _check_cuda(*ts):
@@ -96,7 +97,8 @@ class _EmbedLoss(torch.autograd.Function):
         accum = torch.empty(2, device=dev, dtype=torch.float64)
         loss = torch.empty((), device=dev, dtype=torch.float32)
         st = _lib.stream()
-        call("szn_embed_loss_fwd", kind, ptr(sc), ptr(tg), ptr(te), ptr(tb), n, c, h, w, ptr(stats), ptr(accum),
+        rows = 0 if tb is None else tb.shape[0]  # labels >= rows poison the loss with NaN instead of reading past the table
+        call("szn_embed_loss_fwd", kind, ptr(sc), ptr(tg), ptr(te), ptr(tb), rows, n, c, h, w, ptr(stats), ptr(accum),
              ptr(loss), st)
         if accum_hook is not None:  # e.g. all-reduce of {sum, n_valid} across data-parallel ranks
             accum_hook(accum)
@@ -110,8 +112,8 @@ class _EmbedLoss(torch.autograd.Function):
         n, c, h, w = sc.shape
         g = torch.empty_like(sc)
         go = gout.detach().contiguous().float()
-        call("szn_embed_loss_bwd", kind, ptr(sc), ptr(tg), ptr(te), ptr(tb), n, c, h, w, ptr(stats), ptr(accum),
-             ptr(go), ptr(g), _lib.stream())
+        call("szn_embed_loss_bwd", kind, ptr(sc), ptr(tg), ptr(te), ptr(tb), 0 if tb is None else tb.shape[0], n, c, h, w,
+             ptr(stats), ptr(accum), ptr(go), ptr(g), _lib.stream())
         return g, None, None, None, None, None
 
 
