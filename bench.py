@@ -46,7 +46,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    0: dict(B=1, H=256, D=21, C=21, precision="tf32", loss="ce",
+    0: dict(B=1, H=256, D=21, C=21, precision="fp32", loss="ce",  # the plumbing / parity case runs in the fp32-grade mode
             name="configs[0]: 1x3x256x256 PASCAL-VOC 21-class FCN32s forward + cross_entropy2d(sum) + backward (plumbing)"),
     1: dict(B=8, H=512, D=300, C=59, precision="tf32", loss="cos",
             name="configs[1]: PASCAL-Context-shaped 59-class SZN, 300-d, B=8/GPU, 512x512, fp32 storage + TF32 tcgen05 "
@@ -339,8 +339,11 @@ def main():
     reducer = ddp.GradientAllReduce(model)
 
     def rank_batch(r):
-        """Rank r's images (seed + rank), like a sharded loader would hand them out."""
+        """Rank r's images and labels (seed + rank), like a sharded loader would hand them out.  The class table is the
+        dataset's: the same on every rank (rank 0's draw)."""
         x, lab, tab = synth.synth_batch(B, H, W, C, D, seed=1337 + r)
+        if r:
+            tab = synth.synth_batch(B, H, W, C, D, seed=1337)[2]
         if zeroshot:  # phase-1 training images contain seen classes only (pascal_dataset.py:78-84 filters the others)
             seen = torch.tensor([c for c in range(C) if c not in VAL_UNSEEN + TRAIN_UNSEEN])
             lab = torch.where(lab >= 0, seen[lab.clamp_min(0) % len(seen)], lab)

@@ -82,6 +82,56 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Cfg c, long long* cycles_
   if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
+// CTA pair (cta_group::2): M = 256 over two SMs, each SM holds 128 rows of A and N/2 rows of B.  cycles per pair-MMA as seen
+// by the leader; per SM the instruction does 128 x N x K MACs, like the single-CTA M = 128 instruction.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe2_kernel(Cfg c, long long* cycles_out) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t a0 = smem_u32(raw);
+  uint8_t* smem = raw + ((1024u - (a0 & 1023u)) & 1023u);
+  constexpr int A_BYTES = 128 * 128, B_BYTES = 256 * 128, STAGES = 4;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < STAGES * (A_BYTES + B_BYTES) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp_idx() == 0) {
+    tmem_alloc2(tptr, 512);
+    tmem_relinquish2();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+  const uint32_t idesc = umma_idesc(c.tf32 ? 2 : 1, 0, 0, 256, c.N);
+  const uint32_t a_base = smem_u32(smem), b_base = a_base + STAGES * A_BYTES;
+  const int acc_cols = c.N < 32 ? 32 : c.N;
+  if (rank == 0 && warp_idx() == 0) {
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int it = 0; it < c.iters; ++it) {
+        const int s = it & (STAGES - 1), k = (it >> 2) & 3, acc = it & (c.nacc - 1);
+        const uint64_t ad = umma_desc_sw128(a_base + s * A_BYTES + k * 32, 16, 1024);
+        const uint64_t bd = umma_desc_sw128(b_base + s * B_BYTES + k * 32, 16, 1024);
+        if (c.tf32) tc_mma2<true>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
+        else tc_mma2<false>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
+      }
+      tc_commit2(bar, 1);  // the leader's barrier only
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    if (threadIdx.x == 0) cycles_out[blockIdx.x] = clock64() - t0;
+  } else if (threadIdx.x == 0) {
+    cycles_out[blockIdx.x] = 0;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp_idx() == 0) tmem_dealloc2(tmem, 512);
+}
+
 int main() {
   int dev = 0, sms = 0, khz = 0;
   cudaGetDevice(&dev);
@@ -125,6 +175,34 @@ int main() {
           printf("%-5s %4d %4d %5d | %10.1f | %10.0f | %.2fx%s\n", tf32 ? "tf32" : "bf16", c.M, c.N, c.nacc, cyc,
                  (double)c.M * c.N * kk / cyc, cyc / floor_c, issue ? "" : "   [threadIdx.x == 0 issue]");
         }
+  // ---- CTA pairs ----
+  if (cudaFuncSetAttribute(probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    printf("cudaFuncSetAttribute (pair) failed\n");
+    return 1;
+  }
+  printf("cta_group::2 (M = 256 over a CTA pair; MAC/cyc/SM counts 128 x N x K per SM)\n");
+  for (int tf32 = 1; tf32 >= 0; --tf32)
+    for (int ni = 1; ni < 5; ++ni)
+      for (int ai = 0; ai < 2; ++ai) {
+        Cfg c{tf32, 256, Ns[ni], accs[ai], 4096, 2};
+        const int acc_cols = c.N < 32 ? 32 : c.N;
+        if (c.nacc * acc_cols > 512) continue;
+        for (int rep = 0; rep < 2; ++rep) {
+          probe2_kernel<<<sms & ~1, 128, smem>>>(c, d);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) {
+            printf("pair launch failed (%s) for kind=%s N=%d nacc=%d\n", cudaGetErrorString(e), tf32 ? "tf32" : "bf16", c.N, c.nacc);
+            return 1;
+          }
+        }
+        cudaMemcpy(h, d, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+        long long worst = 0;
+        for (int i = 0; i < (sms & ~1); ++i) worst = h[i] > worst ? h[i] : worst;
+        const double cyc = (double)worst / c.iters;
+        const int kk = tf32 ? 8 : 16;
+        printf("%-5s %4d %4d %5d | %10.1f | %10.0f | %.2fx of N/2\n", tf32 ? "tf32" : "bf16", c.M, c.N, c.nacc, cyc,
+               128.0 * c.N * kk / cyc, cyc / (c.N / 2.0));
+      }
   cudaFree(d);
   free(h);
   return 0;
