@@ -60,6 +60,10 @@ int szn_conv_dgrad(int dtype, const void* dy, const void* wt_dgrad, void* dx, in
 int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int R,
                    int S, int pad, long long ld_dy, void* stream);
 
+/* split-K work items per persistent CTA of szn_conv_wgrad (default 1; data-parallel runs use 3 so that SMs shared with the
+ * gradient all-reduce kernels do not set the kernel's duration -- the tiles are handed out by a global work counter) */
+int szn_set_wgrad_waves(int waves);
+
 /* ---- conv1_1 (models.py:43-44,116): Cin=3, pad=100, CUDA cores; x is the public NCHW fp32 image ---- */
 int szn_conv1_1_fwd(int dtype, const float* x, const float* w_oihw, const float* bias, void* y, int B, int H, int W,
                     int pad, void* stream);

@@ -266,3 +266,33 @@ def test_state_dict_and_get_parameters_contract():
     for _, mod in m.named_modules():
         assert isinstance(mod, allowed)
     assert m.upscore.bias is None and m.seenmask_upscore.bias is None
+
+
+def test_upscore_weight_grad_matches_the_reference_when_asked_for():
+    """trainer_fcn.py:161-162 prints ``self.model.upscore.weight.grad.sum()``: autograd populates the dense (D,D,64,64)
+    gradient of the never-optimised deconv (train.py:324-327).  FCN32s(upscore_weight_grad=True) reproduces it (a
+    213 GFLOP/image job at D=300, hence opt-in); the default leaves ``upscore.weight.grad`` None -- the documented
+    deviation: the filter is frozen, and its diagonal-bilinear structure is what makes the x32 upsample a 4-tap kernel."""
+    from zeroshotsemanticsegmentation_b200 import utils as U
+    import zeroshotsemanticsegmentation_b200 as szn
+    D, C, H, W, B = 20, 21, 40, 56, 2
+    params = O.init_params(D, seed=11)
+    x, lab, table = O.synth_batch(B, H, W, C, D, seed=11, block=8)
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    f_ref = O.forward(x, pr, "fcn")
+    O.cosine_loss(f_ref, lab, O.target_embed_from_labels(lab, table)).backward()
+    for flag in (True, False):
+        m = szn.FCN32s(D, precision="fp32", upscore_weight_grad=flag)
+        m.load_state_dict(params)
+        m = m.to(DEV).eval()
+        f = m(x.to(DEV))
+        U.cosine_loss(f, lab.to(DEV), table=table.to(DEV)).backward()
+        if not flag:
+            assert m.upscore.weight.grad is None
+            continue
+        g, g_ref = m.upscore.weight.grad.cpu(), pr["upscore.weight"].grad
+        assert g.shape == (D, D, 64, 64)
+        e = rel(g.numpy(), g_ref.numpy())
+        print("upscore.weight.grad rel err", e, " sum", float(g.sum()), "vs", float(g_ref.sum()))
+        assert e < 1e-3
+        assert abs(float(g.sum()) - float(g_ref.sum())) < 1e-3 * max(1.0, abs(float(g_ref.abs().sum())))

@@ -17,6 +17,7 @@ SIGNATURES = {
     "szn_conv_fwd": [I, P, P, P, P, I, I, I, I, I, I, I, I, I, P, I, I, LL, P],
     "szn_conv_dgrad": [I, P, P, P, I, I, I, I, I, I, I, I, P, P, I, LL, P, P],
     "szn_conv_wgrad": [I, P, P, P, I, I, I, I, I, I, I, I, LL, P],
+    "szn_set_wgrad_waves": [I],
     "szn_conv1_1_fwd": [I, P, P, P, P, I, I, I, I, P],
     "szn_conv1_1_wgrad": [I, P, P, P, I, I, I, I, P],
     "szn_pool_fwd": [I, P, P, I, I, I, I, P],

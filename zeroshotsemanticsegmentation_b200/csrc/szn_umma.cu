@@ -62,6 +62,8 @@ struct UmmaParams {
   int relu, out_fp32;
   int vec_ok;  // bias / scale rows are 16-byte aligned
   float* col_sum;  // dgrad: += column sums of the stored output (the producer layer's bias gradient) or null
+  unsigned int* sched;  // {next tile, CTAs done}: global work counter of this launch (self-resetting, see launch())
+  int static_tiles;     // tuning / A-B switch (SZN_STATIC_TILES=1): round-robin tile list instead of the work counter
 };
 
 template <typename T>
@@ -130,8 +132,13 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) 
   return t;
 }
 
-// Persistent, warp-specialised implicit-GEMM kernel.  grid = min(#tiles, #SMs); every role walks the same static
-// tile sequence (tile = blockIdx.x + i * gridDim.x).  Three pipelines:
+// Persistent, warp-specialised implicit-GEMM kernel.  grid = min(#tiles, #SMs).  Tiles are handed out DYNAMICALLY: a CTA's
+// first tile is blockIdx.x, every further one comes from a global atomic counter, fetched by the producer warp (one tile
+// ahead, so the atomic's latency hides behind the loads) and passed to the MMA and epilogue warps through a 4-deep
+// shared-memory queue.  A CTA that starts late or runs slowly -- its SM is shared with NCCL's all-reduce kernels, or was
+// still busy with the previous kernel's tail -- simply takes fewer tiles instead of setting the kernel's duration, which is
+// what a static round-robin list did (8-GPU step 22.5 -> 24.5 ms in round 1).  Pipelines:
+//   tile queue  sqf[q]/sqe[q]          TMA producer  -> MMA issuer, epilogue warps
 //   smem ring   full[s]/empty[s]       TMA producer  -> MMA issuer
 //   TMEM        accf[2]/acce[2]        MMA issuer    -> epilogue (two accumulator buffers: the epilogue of tile i
 //                                                       overlaps the main loop of tile i+1)
@@ -166,7 +173,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty = full + 8;
   uint64_t* accf = empty + 8;  // [2] accumulator buffer complete
   uint64_t* acce = accf + 2;   // [2] accumulator buffer drained
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(acce + 2);
+  constexpr int SQ = 4;        // depth of the tile queue
+  uint64_t* sqf = acce + 2;    // [SQ] tile index published by the producer warp
+  uint64_t* sqe = sqf + SQ;    // [SQ] tile index read by the MMA warp and the four epilogue warps
+  int* sq_tile = reinterpret_cast<int*>(sqe + SQ);  // [SQ] tile index, -1 = no more work
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(sq_tile + SQ);
 
   const int warp = warp_idx(), lane = threadIdx.x & 31;  // provably warp-uniform (see elect_one)
 
@@ -183,6 +194,10 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&accf[i], 1);
       mbar_init(&acce[i], 4);  // one arrival per epilogue warp
+    }
+    for (int i = 0; i < SQ; ++i) {
+      mbar_init(&sqf[i], 1);
+      mbar_init(&sqe[i], 5);  // MMA warp + four epilogue warps
     }
     fence_mbar_init();
   }
@@ -210,7 +225,20 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t box_tx = (uint32_t)(p.gpt * rows_a * 128);  // MODE 2: bytes of one B box
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int tile = blockIdx.x, nxt = 0;
+    for (uint32_t qi = 0;; ++qi) {
+      // publish this tile (or the end marker) to the other roles
+      const int slot = qi & (SQ - 1);
+      mbar_wait(&sqe[slot], ((qi / SQ) & 1u) ^ 1u);
+      const bool live = tile < p.total_tiles;
+      if (lane == 0) {
+        sq_tile[slot] = live ? tile : -1;
+        mbar_arrive(&sqf[slot]);
+        // claim the next tile right away: the atomic's round trip hides behind this tile's loads
+        if (live) nxt = p.static_tiles ? tile + (int)gridDim.x : (int)atomicAdd(p.sched, 1u) + (int)gridDim.x;
+      }
+      __syncwarp();
+      if (!live) break;
       const TileCoord t = decode_tile<MODE>(p, tile);
       int tap = 0, cc = 0, r = 0, sx = 0;  // MODE 0: filter tap (r, sx) and channel chunk
       int bb = 0, py0 = 0, px0 = 0;        // MODE 2: pixel chunk (image, tile origin)
@@ -276,6 +304,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      tile = __shfl_sync(0xffffffffu, nxt, 0);
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
@@ -284,7 +313,13 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int s = 0;
     uint32_t ph = 0;
     uint32_t local = 0;  // tiles this CTA has started: accumulator buffer = local & 1
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (uint32_t qi = 0;; ++qi) {
+      const int slot = qi & (SQ - 1);
+      mbar_wait(&sqf[slot], (qi / SQ) & 1u);
+      const int tile = sq_tile[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sqe[slot]);
+      if (tile < 0) break;
       const TileCoord t = decode_tile<MODE>(p, tile);
       if (t.n_iters == 0) continue;
       const uint32_t buf = p.nbuf == 2 ? (local & 1u) : 0u, aph = p.nbuf == 2 ? ((local >> 1) & 1u) : (local & 1u);
@@ -379,15 +414,17 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     };
 
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (uint32_t qi = 0;; ++qi) {
+      const int slot = qi & (SQ - 1);
+      mbar_wait(&sqf[slot], (qi / SQ) & 1u);
+      const int tile = sq_tile[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sqe[slot]);
+      if (tile < 0) break;
       const TileCoord t = decode_tile<MODE>(p, tile);
       if (t.n_iters == 0) continue;
       const uint32_t buf = p.nbuf == 2 ? (local & 1u) : 0u, aph = p.nbuf == 2 ? ((local >> 1) & 1u) : (local & 1u);
       ++local;
-      mbar_wait(&accf[buf], aph);
-      tc_fence_after();
-      const uint32_t tbase = tmem + buf * (uint32_t)p.tmem_cols + ((uint32_t)(q4 * 32) << 16);
-
       bool ok = true;
       size_t orow = 0;  // output row index (pixel) for the mask / scale lookups
       int img = 0;
@@ -398,6 +435,27 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         orow = ((size_t)t.b * p.H + y) * p.W + x;
         img = ok ? (int)(orow / (size_t)p.pix_per_image) : 0;  // rows outside the image are clipped by the store
       }
+      // dgrad: the ReLU-gate row of a chunk (128 bytes of the consumer activation) does not depend on the accumulator:
+      // it is fetched one chunk ahead -- the first one before waiting for the MMAs -- so its global-memory latency hides
+      // behind the TMEM load / staging / store of the previous chunk instead of stalling every chunk (dgrad ran 7-30 %
+      // behind the forward pass of the same shape).  Not in the split format (254 registers already).
+      constexpr bool PREF = MODE != 2 && !SPLIT;
+      uint4 mrow[PREF ? 8 : 1];
+      bool mrow_ok = false;  // mrow holds the whole row of the chunk about to be processed
+      auto prefetch_mask = [&](int nb_) {
+        mrow_ok = false;
+        if (PREF && p.mask_ref && ok && nb_ + CW <= p.N) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.mask_ref) + orow * p.ld_mask + nb_);
+#pragma unroll
+          for (int j = 0; j < (PREF ? 8 : 1); ++j) mrow[j] = __ldg(r4 + j);
+          mrow_ok = true;
+        }
+      };
+      if (PREF) prefetch_mask(t.n0);
+      mbar_wait(&accf[buf], aph);
+      tc_fence_after();
+      const uint32_t tbase = tmem + buf * (uint32_t)p.tmem_cols + ((uint32_t)(q4 * 32) << 16);
+
       const int n_chunks = (block_n + CW - 1) / CW;
       for (int hc = 0; hc < mp * n_chunks; ++hc) {
         const int h = hc / n_chunks, c = hc - h * n_chunks;  // h: 128-row sub-tile (MODE 2 with mpair = 2)
@@ -469,7 +527,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (TF32) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const uint4 u = __ldg(r4 + j);
+                  const uint4 u = (PREF && mrow_ok) ? mrow[j % (PREF ? 8 : 1)] : __ldg(r4 + j);
                   if (!(__uint_as_float(u.x) > 0.f)) f[4 * j + 0] = 0.f;
                   if (!(__uint_as_float(u.y) > 0.f)) f[4 * j + 1] = 0.f;
                   if (!(__uint_as_float(u.z) > 0.f)) f[4 * j + 2] = 0.f;
@@ -478,7 +536,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const uint4 u = __ldg(r4 + j);
+                  const uint4 u = (PREF && mrow_ok) ? mrow[j % (PREF ? 8 : 1)] : __ldg(r4 + j);
                   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
@@ -496,6 +554,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (j < nvalid && !(load_as_float<T>(ref + j) > 0.f)) f[j] = 0.f;
             }
           }
+          if (PREF && p.mask_ref && hc + 1 < mp * n_chunks) prefetch_mask(nb + CW);  // next chunk's gate row
         }
         // ---- registers -> staging -> TMA store ----
         uint4 q[8];
@@ -579,6 +638,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, (uint32_t)(p.nbuf * p.tmem_cols));
+  if (threadIdx.x == 0) {
+    // the last CTA to leave re-arms the work counter for the next launch that uses this slot
+    __threadfence();
+    if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {
+      p.sched[0] = 0u;
+      p.sched[1] = 0u;
+      __threadfence();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -671,12 +739,27 @@ static int num_sms() {
   return n;
 }
 
+// work counters of the dynamic tile scheduler: {next, done} pairs, zero at module load and re-armed by the kernel itself.
+// Launches take the slots round-robin, so kernels that overlap on different streams do not share a counter.
+constexpr int SCHED_SLOTS = 256;
+__device__ unsigned int g_sched[2 * SCHED_SLOTS];
+
+static unsigned int* sched_slot() {
+  static unsigned int* base[64] = {nullptr};
+  static unsigned int seq = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!base[dev] && cudaGetSymbolAddress(reinterpret_cast<void**>(&base[dev]), g_sched) != cudaSuccess) return nullptr;
+  return base[dev] + 2 * (seq++ % SCHED_SLOTS);
+}
+
 template <typename T, int MODE, bool SPLIT>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, UmmaParams& p, long long tiles,
                   cudaStream_t st) {
   if (MODE != 2 || p.mpair < 1 || SPLIT) p.mpair = 1;
   const int stage_bytes = (SPLIT ? 2 : 1) * (128 * 128 * p.mpair + p.block_n * 128);
-  const int fixed = 2 * 128 * 128 /* epilogue staging */ + 1024 /* alignment */ + 256 /* barriers */;
+  const int fixed = 2 * 128 * 128 /* epilogue staging */ + 1024 /* alignment */ + 384 /* barriers, tile queue */;
   int stages = (227 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return set_error(SZN_ERR_UNSUPPORTED, "conv: tile does not leave two pipeline stages");
@@ -694,6 +777,13 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
   p.tmem_cols = p.acc_cols * p.mpair * p.nacc;  // per accumulator buffer
   p.nbuf = 2 * p.tmem_cols <= 512 ? 2 : 1;
   p.total_tiles = (int)tiles;
+  {
+    static int st = -1;
+    if (st < 0) st = getenv("SZN_STATIC_TILES") ? 1 : 0;
+    p.static_tiles = st;
+  }
+  p.sched = sched_slot();
+  if (!p.sched) return set_error(SZN_ERR_CUDA, "conv: no work counter (cudaGetSymbolAddress failed)");
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool attr_set = false;
   if (!attr_set) {
@@ -848,6 +938,24 @@ static void pick_tile_k(int W, int H, int max_rows, int step, int* TW, int* TH) 
   *TH = bh;
 }
 
+// split-K work items per CTA of the weight gradient.  1 (default) is fastest on an otherwise idle GPU (measured 5.30 / 5.38 /
+// 5.46 / 5.54 ms per step for 1 / 2 / 3 / 4: every item ends with a reduce-add pass over its output tile); data-parallel
+// runs use 3, so that a CTA whose SM is busy with NCCL's kernels costs a third of a tile list, not a whole one.
+static int g_wgrad_waves = 0;
+static int wgrad_waves() {
+  if (!g_wgrad_waves) {
+    const char* e = getenv("SZN_WGRAD_WAVES");
+    g_wgrad_waves = e ? atoi(e) : 1;
+    if (g_wgrad_waves < 1) g_wgrad_waves = 1;
+  }
+  return g_wgrad_waves;
+}
+extern "C" int szn_set_wgrad_waves(int waves) {
+  if (waves < 1 || waves > 16) return set_error(SZN_ERR_ARG, "szn_set_wgrad_waves: 1..16");
+  g_wgrad_waves = waves;
+  return 0;
+}
+
 extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* dw, int B, int H, int W, int Cin,
                               int Cout, int R, int S, int pad, long long ld_dy, void* stream) {
   if (dtype != SZN_F32 && dtype != SZN_BF16 && dtype != SZN_F32X3) return set_error(SZN_ERR_ARG, "szn_conv_wgrad: bad dtype");
@@ -892,12 +1000,7 @@ extern "C" int szn_conv_wgrad(int dtype, const void* x, const void* dy, float* d
   p.m_tiles = ceil_div(Cout, 128 * p.mpair);
   const long long total_q = (long long)p.tiles_x * p.tiles_y * Bq;
   const long long tiles = (long long)p.n_tiles * p.m_tiles;
-  static int waves = 0;
-  if (!waves) {
-    const char* e = getenv("SZN_WGRAD_WAVES");  // tuning hook
-    waves = e ? atoi(e) : 1;  // measured 5.30 / 5.38 / 5.46 / 5.54 ms for 1 / 2 / 3 / 4
-    if (waves < 1) waves = 1;
-  }
+  const int waves = wgrad_waves();
   // `waves` work items per CTA, rounded DOWN so that no CTA gets one item more than the others (rounding up gave
   // e.g. 297 items for 148 CTAs: one CTA with 3 items set the kernel's duration)
   long long splits = ((long long)waves * num_sms()) / tiles;

@@ -10,6 +10,8 @@ NCCL's own stream, so the transfers overlap the remaining dgrad/wgrad kernels; t
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -29,6 +31,11 @@ class GradientAllReduce:
         if self.enabled:
             model._grad_ready = self._on_ready
             model._grad_flush = self._flush
+            if torch.cuda.is_available():
+                # the all-reduce kernels share the SMs with the backward pass: finer split-K work items let the dynamic
+                # tile scheduler route around busy SMs (include/szn.h: szn_set_wgrad_waves)
+                from . import _lib
+                _lib.call("szn_set_wgrad_waves", int(os.environ.get("SZN_DDP_WGRAD_WAVES", "3")))
             if sync_params:
                 self.broadcast_parameters()
 
