@@ -525,11 +525,12 @@ def main():
 
     clk_path = os.path.join(tempfile.gettempdir(), "szn_clocks_%d.csv" % rank)
     sampler = clocks_sampler(clk_path) if rank == 0 else None
-    bytes0 = reducer.bytes_reduced
+    bytes0, nccl0 = reducer.bytes_reduced, reducer.launches
     n0 = _lib.launch_count()
     ms_total = timed(resident, args.steps)
     launches = _lib.launch_count() - n0
     allreduce_bytes = (reducer.bytes_reduced - bytes0) // max(1, args.steps)
+    allreduce_launches = (reducer.launches - nccl0) / max(1, args.steps)
     e2e_ms = None
     if not args.no_e2e:
         for _ in range(2):
@@ -698,6 +699,9 @@ def main():
         out["loss"] = float(last["loss"].item())
     if world > 1:
         out["allreduce_bytes_per_step"] = int(allreduce_bytes)
+        out["allreduce"] = {"path": "szn_allreduce_bucket (C ABI, own NCCL communicator, one fused launch per bucket, side stream)"
+                            if reducer.comm is not None else "torch.distributed.all_reduce per tensor",
+                            "bucket_launches_per_step": allreduce_launches}
         if grad_check is not None:
             out["grad_check"] = grad_check
         dist.barrier()

@@ -176,6 +176,18 @@ int szn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int szn_confusion_hist(const long long* label_true, const long long* label_pred, long long n, int n_class,
                        const unsigned char* is_unseen, long long* hist, void* stream);
 
+/* ---- data parallelism: the one exchange step of the path, all-reduce(sum) of parameter gradients.  The
+ * reference has no distributed code; this is what a maintainer binds for N > 1.  The communicator is NCCL's, created from a
+ * 128-byte unique id that rank 0 obtains and the caller ships to every rank (ddp.py uses torch.distributed for that).  NCCL
+ * is resolved at run time from the libnccl.so.2 already in the process; szn_comm_available() says whether it was found. */
+int szn_comm_available(void);
+int szn_comm_unique_id(char* id128);
+int szn_comm_init(const char* id128, int rank, int world, void** comm_out);
+int szn_comm_destroy(void* comm);
+/* one bucket: n device buffers (bufs[i], counts[i] elements of `dtype`: SZN_F32, SZN_BF16 or 3 = fp64) summed over the
+ * ranks in place, inside one NCCL group (one fused launch) on `stream`.  bufs / counts are HOST arrays. */
+int szn_allreduce_bucket(void* comm, void* const* bufs, const long long* counts, int n, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

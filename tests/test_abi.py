@@ -25,7 +25,8 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "libszn.so does not export %s" % n
     # every bound signature is declared in the header and vice versa
     assert set(_lib.SIGNATURES) | {"szn_last_error", "szn_launch_count", "szn_abi_version",
-                                   "szn_embed_argmax_scratch_floats", "szn_head_fused_workspace_floats"} == set(names)
+                                   "szn_embed_argmax_scratch_floats", "szn_head_fused_workspace_floats",
+                                   "szn_comm_available"} == set(names)
 
 
 def test_no_cpu_fallback():

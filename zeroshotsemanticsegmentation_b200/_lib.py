@@ -18,6 +18,10 @@ SIGNATURES = {
     "szn_conv_dgrad": [I, P, P, P, I, I, I, I, I, I, I, I, P, P, I, LL, P, P],
     "szn_conv_wgrad": [I, P, P, P, I, I, I, I, I, I, I, I, LL, P],
     "szn_set_wgrad_waves": [I],
+    "szn_comm_unique_id": [P],
+    "szn_comm_init": [P, I, I, P],
+    "szn_comm_destroy": [P],
+    "szn_allreduce_bucket": [P, P, P, I, I, P],
     "szn_conv1_1_fwd": [I, P, P, P, P, I, I, I, I, P],
     "szn_conv1_1_wgrad": [I, P, P, P, I, I, I, I, P],
     "szn_pool_fwd": [I, P, P, I, I, I, I, P],
@@ -72,6 +76,7 @@ def load():
     lib.szn_embed_argmax_scratch_floats.argtypes = [I, I]
     lib.szn_embed_argmax_scratch_floats.restype = LL
     lib.szn_abi_version.restype = I
+    lib.szn_comm_available.restype = I
     lib.szn_head_fused_workspace_floats.argtypes = [I, I, I, I]
     lib.szn_head_fused_workspace_floats.restype = LL
     _lib = lib
@@ -87,10 +92,34 @@ def set_profiler(fn):
     _profiler = fn
 
 
+NVTX = os.environ.get("SZN_NVTX") == "1"  # SZN_NVTX=1: an NVTX range per layer (engine.py) and per C-ABI call
+
+
+class nvtx_range:
+    """``with nvtx_range("conv3_2 fwd"):`` -- a no-op unless SZN_NVTX=1 (nsys / ncu --nvtx show the layer structure)."""
+
+    def __init__(self, label):
+        self.label = label
+
+    def __enter__(self):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_push(self.label)
+
+    def __exit__(self, *exc):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_pop()
+
+
 def call(name, *args):
     lib = load()
     done = _profiler(name, args) if _profiler is not None else None
-    rc = getattr(lib, name)(*args)
+    if NVTX:
+        with nvtx_range(name):
+            rc = getattr(lib, name)(*args)
+    else:
+        rc = getattr(lib, name)(*args)
     if done is not None:
         done()
     if rc != 0:

@@ -193,8 +193,9 @@ class FCN32sFunction(torch.autograd.Function):
             else:
                 _, cin, cout, k, pad = row
                 o = torch.empty((B, h, w_, npl * cout), device=dev, dtype=tdtype)
-                call("szn_conv_fwd", dt, ptr(a), ptr(packed(name)), ptr(P[name + ".bias"].detach()), ptr(o),
-                     B, h, w_, cin, cout, k, k, pad, 1, None, 0, 0, cout, st)
+                with _lib.nvtx_range(name + " fwd"):
+                    call("szn_conv_fwd", dt, ptr(a), ptr(packed(name)), ptr(P[name + ".bias"].detach()), ptr(o),
+                         B, h, w_, cin, cout, k, k, pad, 1, None, 0, 0, cout, st)
                 c = cout
             a = o
             acts[name], dims[name] = a, (h, w_, c)
@@ -367,7 +368,8 @@ class FCN32sFunction(torch.autograd.Function):
             ho, wo = xh + 2 * pad - k + 1, xw + 2 * pad - k + 1
             if need[name + ".weight"]:
                 dw = zeros((cout, k * k, cin))
-                call("szn_conv_wgrad", dt, ptr(x_act), ptr(dy), ptr(dw), B, xh, xw, cin, cout, k, k, pad, cout, st)
+                with _lib.nvtx_range(name + " wgrad"):
+                    call("szn_conv_wgrad", dt, ptr(x_act), ptr(dy), ptr(dw), B, xh, xw, cin, cout, k, k, pad, cout, st)
                 # dW lives as [Cout][R][S][Cin]; hand autograd the OIHW-shaped *view* of it (channels_last strides):
                 # same values, no unpack pass over 135 M gradients
                 grads[name + ".weight"] = dw.view(cout, k, k, cin).permute(0, 3, 1, 2)
@@ -389,9 +391,10 @@ class FCN32sFunction(torch.autograd.Function):
                      0, None, None, 0, cout, None, st)
                 call("szn_col2im", dt, ptr(dcol), ptr(dx), B, xh, xw, cin, k, k, st)
                 return dx
-            call("szn_conv_dgrad", dt, ptr(dy), ptr(packed_d(name)), ptr(dx), B, xh, xw, cin, cout, k, k, pad,
-                 ptr(relu_ref), ptr(scale), 4096 if scale is not None else 0, cout,
-                 ptr(db_buffer(producer)) if producer is not None else None, st)
+            with _lib.nvtx_range(name + " dgrad"):
+                call("szn_conv_dgrad", dt, ptr(dy), ptr(packed_d(name)), ptr(dx), B, xh, xw, cin, cout, k, k, pad,
+                     ptr(relu_ref), ptr(scale), 4096 if scale is not None else 0, cout,
+                     ptr(db_buffer(producer)) if producer is not None else None, st)
             return dx
 
         n_convs = len(CONV_NAMES)
