@@ -97,3 +97,13 @@ def test_model_with_fused_head_equals_default_path():
     m = m.to(DEV).eval()
     f = m(x, mode="fcn")
     assert U._fused_handle(f) is not None and U._fused_handle(f.detach()) is None and U._fused_handle(f * 1.0) is None
+    # the loss pass leaves the labels of (this score, this table) behind; infer_lbl picks them up, another table does not
+    head = U._fused_handle(f)
+    assert getattr(head, "labels_cache", None) is None
+    fresh = U.infer_lbl_device(f, table)            # label-only launch
+    U.cosine_loss(f, lab, table=table)
+    assert head.labels_cache is not None
+    cached = U.infer_lbl_device(f, table)
+    assert cached is head.labels_cache[3] and torch.equal(cached, fresh)
+    other = table.flip(0).contiguous()
+    assert not torch.equal(U.infer_lbl_device(f, other), cached)

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(256) fused_pixels_kernel(const float* __restri
       if (labels) labels[pix] = bi;
       if (LOSS) {
         const long long t = target[pix];
+        if (t >= C) part += (double)NAN, cnt += 1.0;  // out-of-range label: poison the loss (like szn_embed_loss_fwd)
         if (t >= 0 && t < C) {
           const float pat = fmaf(w0, Ac[t], fmaf(w1, Ac[C + t], fmaf(w2, Ac[2 * C + t], w3 * Ac[3 * C + t])));
           const float un2 = w0 * w0 * Gc[0] + w1 * w1 * Gc[1] + w2 * w2 * Gc[2] + w3 * w3 * Gc[3] +

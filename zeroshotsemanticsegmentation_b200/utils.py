@@ -134,7 +134,7 @@ class _FusedHeadLoss(torch.autograd.Function):
     input and gradient are [B,hs,ws,Dp] fp32, the (B, D, H, W) score tensor is not touched."""
 
     @staticmethod
-    def forward(ctx, s17, target, table, D, hw, accum_hook, kind=0):
+    def forward(ctx, s17, target, table, D, hw, accum_hook, kind=0, head=None):
         _check_cuda(s17, target, table)
         B, hs, ws, ld = s17.shape
         H, W = hw
@@ -148,8 +148,13 @@ class _FusedHeadLoss(torch.autograd.Function):
         accum = torch.empty(2, device=sc.device, dtype=torch.float64)
         loss = torch.empty((), device=sc.device, dtype=torch.float32)
         st = _lib.stream()
+        # the loss pass scans every class of every pixel anyway: it also writes the nearest-embedding labels, which
+        # infer_lbl* on the same score and table then simply picks up (trainer_fcn.py:100-117 calls both every iteration)
+        labels = torch.empty((B, H, W), device=sc.device, dtype=torch.int64) if head is not None else None
         call("szn_head_fused_fwd", kind, ptr(sc), ld, 0, ptr(tg), ptr(tb), B, D, H, W, hs, ws, C, ptr(work), ptr(accum),
-             ptr(loss), None, st)
+             ptr(loss), ptr(labels), st)
+        if head is not None:
+            head.labels_cache = (table.data_ptr(), table._version, tuple(table.shape), labels)
         if accum_hook is not None:
             accum_hook(accum)
             call("szn_loss_finalize", kind, ptr(accum), ptr(loss), st)
@@ -164,7 +169,7 @@ class _FusedHeadLoss(torch.autograd.Function):
         go = gout.detach().contiguous().float()
         call("szn_head_fused_bwd", kind, ptr(sc), ld, 0, ptr(tb), B, D, hs, ws, tb.shape[0], ptr(work), ptr(accum), ptr(go),
              ptr(ds), _lib.stream())
-        return ds, None, None, None, None, None, None
+        return ds, None, None, None, None, None, None, None
 
 
 class _CrossEntropy2d(torch.autograd.Function):
@@ -208,16 +213,16 @@ def cross_entropy2d(score, target, weight=None, size_average=False, accum_hook=N
 def mse_loss(score, target, target_embed=None, table=None, accum_hook=None):
     """sum over valid pixels and channels of (score - target_embed)^2 / n_valid (``utils.py:50-73``)."""
     head = _fused_handle(score) if target_embed is None and table is not None else None
-    if head is not None:  # experimental FCN32s(fused_head=True)
-        return _FusedHeadLoss.apply(head.s17, target, table, head.D, head.hw, accum_hook, 1)
+    if head is not None:  # FCN32s(fused_head=True)
+        return _FusedHeadLoss.apply(head.s17, target, table, head.D, head.hw, accum_hook, 1, head)
     return _EmbedLoss.apply(score, target, target_embed, table, 1, accum_hook)
 
 
 def cosine_loss(score, target, target_embed=None, table=None, accum_hook=None):
     """(N - sum_valid cos(score_p, target_embed_p)) / N (``utils.py:75-102``)."""
     head = _fused_handle(score) if target_embed is None and table is not None else None
-    if head is not None:  # experimental FCN32s(fused_head=True): work from the 17x17 map the score was upsampled from
-        return _FusedHeadLoss.apply(head.s17, target, table, head.D, head.hw, accum_hook)
+    if head is not None:  # FCN32s(fused_head=True): work from the 17x17 map the score was upsampled from
+        return _FusedHeadLoss.apply(head.s17, target, table, head.D, head.hw, accum_hook, 0, head)
     return _EmbedLoss.apply(score, target, target_embed, table, 0, accum_hook)
 
 
@@ -226,7 +231,10 @@ def _labels_device(score, embed_arr):
     _check_shapes(score, None, None, embed_arr)
     n, c, h, w = score.shape
     head = _fused_handle(score)
-    if head is not None:  # experimental FCN32s(fused_head=True)
+    if head is not None:  # FCN32s(fused_head=True)
+        cached = getattr(head, "labels_cache", None)
+        if cached is not None and cached[:3] == (embed_arr.data_ptr(), embed_arr._version, tuple(embed_arr.shape)):
+            return cached[3]  # written by the loss pass on this score and this table
         s17 = head.s17.detach().contiguous().float()
         tb = _as_f32(embed_arr)
         if tb.shape[1] != c:
