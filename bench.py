@@ -705,7 +705,12 @@ def main():
         if grad_check is not None:
             out["grad_check"] = grad_check
         dist.barrier()
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    cpu_ok = D * D * 64 * 64 * 4 <= 4e9  # the reference's dense upscore weight (models.py:94) is 17 GB at D = 1024
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not cpu_ok:
+        out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                               "sample": "skipped: the reference's dense ConvTranspose2d(D, D, 64, 32) weight alone is %.0f GB at D = %d"
+                                         % (D * D * 64 * 64 * 4 / 1e9, D)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and cpu_ok:
         # CPU arm on the SAME weights and the SAME image 0 as the GPU model, eval mode on both sides: one cold pass gives the
         # baseline time AND this build's full-size parity numbers
         model.eval()

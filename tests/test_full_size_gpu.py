@@ -231,15 +231,16 @@ def _l2(a, b):
     return float((a.detach().cpu().double() - b.double()).norm() / b.double().norm())
 
 
-@pytest.mark.parametrize("init", ["he", "default"])
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision,init", [("fp32", "he"), ("fp32", "default"), ("tf32", "he"), ("tf32", "default"), ("bf16", "he")])
 def test_model_full_size_forward_vs_oracle_and_batch_consistency(precision, init):
     """Full-size forward of one image against the CPU oracle (the reference's fp32 semantics), run alone (B=1) and as
     image 3 of the B=8 batch, under the reference's default init and under the bench's He-style init.
 
     precision="fp32" (3 x bf16 error-compensated products, the parity mode) is held to the north star's 1e-3 STRICTLY, for
     the embedding score f AND the 2-channel seen-mask score s, and its full-size gradients are compared with the oracle.
-    precision="tf32" (the throughput mode) is reported and held to what 16 layers of 2^-11 products can give."""
+    precision="tf32" (the throughput mode) is reported and held to what 16 layers of 2^-11 products can give.
+    precision="bf16" (BASELINE configs[2]-[4]) is narrower than the reference's arithmetic: its 512 x 512 numbers are
+    printed and bounded loosely (forward ~1e-2, labels ~99 %), an honest statement of what that mode is."""
     import zeroshotsemanticsegmentation_b200 as szn
     U = szn.utils
     ref = _oracle_full_size(init)
@@ -260,6 +261,8 @@ def test_model_full_size_forward_vs_oracle_and_batch_consistency(precision, init
         # north star: "outputs match the reference forward within 1e-3 relative": strict, both heads, both inits
         for k in ("f8", "f1", "s8", "s1", "f8_vs_f1", "s8_vs_s1"):
             assert e[k] < 1e-3, (k, e[k])
+    elif precision == "bf16":
+        assert e["f8"] < 3e-2 and e["f1"] < 3e-2 and e["s8"] < 6e-2 and e["s1"] < 6e-2
     else:
         # TF32 (throughput mode): 16 layers of TF32 products and TF32-rounded activations sit AT the bound at full size
         # with the He-style init (measured 9.7e-4; the 2-channel seen-mask score, whose maximum is only ~2 sigma of its
@@ -272,14 +275,15 @@ def test_model_full_size_forward_vs_oracle_and_batch_consistency(precision, init
     l1 = U.infer_lbl_device(f1, table)[0].cpu().numpy()
     agree8, agree1 = float((l8 == l_ref[0]).mean()), float((l1 == l_ref[0]).mean())
     print("end-to-end label agreement with the oracle: B=8 %.5f  B=1 %.5f" % (agree8, agree1))
-    assert agree8 > (0.9995 if precision == "fp32" else 0.99) and agree1 > (0.9995 if precision == "fp32" else 0.99)
+    floor = {"fp32": 0.9995, "tf32": 0.99, "bf16": 0.97}[precision]
+    assert agree8 > floor and agree1 > floor
 
     # ---- full-size gradients of the same image against the oracle (eval mode: no dropout on either side) ----
     m.zero_grad(set_to_none=True)
     f = m(x[3:4].contiguous(), mode="fcn")
     loss = U.cosine_loss(f, lab[3:4], table=table)
     loss.backward()
-    assert abs(loss.item() - ref["loss"]) < (1e-5 if precision == "fp32" else 1e-3)
+    assert abs(loss.item() - ref["loss"]) < {"fp32": 1e-5, "tf32": 1e-3, "bf16": 1e-2}[precision]
     ge, gl = {}, {}
     for n in ("score_fr.weight", "score_fr.bias", "fc7.weight", "fc7.bias", "fc6.bias", "conv5_3.weight", "conv3_1.weight",
               "conv1_2.weight", "conv1_1.weight", "conv1_1.bias"):
@@ -301,8 +305,10 @@ def test_model_full_size_forward_vs_oracle_and_batch_consistency(precision, init
             deep = n.startswith(("conv1", "conv2", "conv3"))
             assert gl[n] < (3e-2 if deep else 1e-2), (n, gl[n])
             assert ge[n] < (1e-1 if deep else 5e-2), (n, ge[n])
-    else:
+    elif precision == "tf32":
         assert ge["score_fr.weight"] < 1e-2 and ge["score_fr.bias"] < 1e-2 and gl["fc7.bias"] < 5e-2
+    else:
+        assert gl["score_fr.weight"] < 5e-2 and gl["fc7.bias"] < 2e-1
 
     if precision == "tf32" and init == "he":
         # whole training step at full size: finite loss and gradients, frozen upscore untouched

@@ -30,6 +30,7 @@
 #include "szn_internal.h"
 #include "szn_ptx.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace szn {
 
@@ -54,6 +55,7 @@ struct UmmaParams {
   long long ldo;          // channels per output row (= its row stride in elements; split: stride of one plane pair / 2)
   long long ld_mask;      // row stride of mask_ref in elements of T (split: 2 * channels, the hi plane comes first)
   int a_lo_goff, b_lo_goff;  // SPLIT, MODE 2: channel-group offset of the lo plane inside a pixel row of dy / x
+  int a_lo_ch;               // SPLIT, MODE 0 im2col: channel offset of the lo plane inside a pixel row of the input (= ldx)
   const float* bias;      // [N] or null
   const float* scale;     // [B][scale_ld] per-(image, channel) multiplier (Dropout2d) or null
   int scale_ld;
@@ -63,6 +65,8 @@ struct UmmaParams {
   int vec_ok;  // bias / scale rows are 16-byte aligned
   float* col_sum;  // dgrad: += column sums of the stored output (the producer layer's bias gradient) or null
   unsigned int* sched;  // {next tile, CTAs done}: global work counter of this launch (self-resetting, see launch())
+  int im2col;           // MODE 0: M tiles are runs of 128 consecutive output pixels, A fetched by im2col-mode TMA
+  long long m_total;    // MODE 0 im2col: output pixels B * Ho * Wo
   int static_tiles;     // tuning / A-B switch (SZN_STATIC_TILES=1): round-robin tile list instead of the work counter
 };
 
@@ -121,6 +125,16 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) 
     if (q_end > total_q) q_end = total_q;
     t.n_iters = q_end - t.q_begin;
     if (t.n_iters < 0) t.n_iters = 0;
+  } else if (p.im2col) {
+    // a run of 128 output pixels starting at linear index m0 = idx * 128 (kept in q_begin); (x0, y0, b) = its first pixel
+    const long long m0 = (long long)idx * 128;
+    const int hw = p.H * p.W;
+    t.b = (int)(m0 / hw);
+    const int r = (int)(m0 - (long long)t.b * hw);
+    t.y0 = r / p.W;
+    t.x0 = r - t.y0 * p.W;
+    t.q_begin = idx;
+    t.n_iters = p.R * p.S * p.kchunks;
   } else {
     t.b = idx / tiles_per_img;
     const int r = idx - t.b * tiles_per_img;
@@ -266,7 +280,19 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* a_dst = smem + s * stage_bytes;
           uint8_t* b_dst = a_dst + NPL * a_bytes;
           mbar_expect_tx(&full[s], NPL * (a_tx + b_tx));
-          if (MODE == 0) {
+          if (MODE == 0 && p.im2col) {
+            // base pixel of the run relative to the tensor (-pad = first output pixel), tap (r, sx) as the im2col offset;
+            // split: a pixel row is [hi | lo], the lo plane's channels simply follow at + Ck
+            tma_load_im2col_4d(a_dst, &tmA, &full[s], cc * KC, t.x0 - p.pad, t.y0 - p.pad, t.b, (uint16_t)sx, (uint16_t)r);
+            if (SPLIT) {
+              tma_load_im2col_4d(a_dst + a_bytes, &tmA, &full[s], p.a_lo_ch + cc * KC, t.x0 - p.pad, t.y0 - p.pad, t.b, (uint16_t)sx,
+                                 (uint16_t)r);
+              tma_load_3d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0, 0);
+              tma_load_3d(b_dst + b_bytes, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0, 1);
+            } else {
+              tma_load_2d(b_dst, &tmB, &full[s], tap * p.Ck + cc * KC, t.n0);
+            }
+          } else if (MODE == 0) {
             if (SPLIT) {  // planes are the 5th (A) / 3rd (B) tensor-map dimension
               tma_load_5d(a_dst, &tmA, &full[s], cc * KC, t.x0 + sx - p.pad, t.y0 + r - p.pad, t.b, 0);
               tma_load_5d(a_dst + a_bytes, &tmA, &full[s], cc * KC, t.x0 + sx - p.pad, t.y0 + r - p.pad, t.b, 1);
@@ -408,6 +434,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       named_bar_sync(1, 128);
       if (issuer) {
         if (MODE == 2) tma_reduce_add_2d(&tmO, sbuf, nb, m_row);
+        else if (p.im2col && SPLIT && !f32_out) tma_store_3d(&tmO, sbuf, nb, t.q_begin * 128, plane);  // {C, pixels, plane}
+        else if (p.im2col) tma_store_2d(&tmO, sbuf, nb, t.q_begin * 128);                               // {C, pixels}
         else if (SPLIT && !f32_out) tma_store_5d(&tmO, sbuf, nb, t.x0, t.y0, t.b, plane);
         else tma_store_4d(&tmO, sbuf, nb, t.x0, t.y0, t.b);
         bulk_commit();
@@ -428,7 +456,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       bool ok = true;
       size_t orow = 0;  // output row index (pixel) for the mask / scale lookups
       int img = 0;
-      if (MODE != 2) {
+      if (MODE != 2 && p.im2col) {
+        orow = (size_t)t.q_begin * 128 + row;  // the tile is a run of consecutive output pixels
+        ok = (long long)orow < p.m_total;
+        img = ok ? (int)(orow / (size_t)p.pix_per_image) : 0;
+      } else if (MODE != 2) {
         const int ty = row / p.TW, tx_ = row - ty * p.TW;
         const int y = t.y0 + ty, x = t.x0 + tx_;
         ok = row < rows_a && y < p.H && x < p.W;
@@ -671,8 +703,38 @@ static EncodeTiledFn get_encode() {
 
 // dims/box innermost first; strides in elements for dims 1..rank-1
 // dtype here is the ELEMENT type of the mapped tensor (SZN_F32 / SZN_BF16)
+// Encoded maps are cached, keyed by (base pointer, element type, rank, dims, strides, box, swizzle): a training loop
+// re-uses the same buffers step after step (the caching allocator hands the same blocks back, weights never move), so
+// after the first step every launch finds its three maps ready instead of making three driver calls.
+struct TmapKey {
+  const void* base;
+  int dtype, rank, mn;
+  long long dims[5], strides[5];
+  int box[5];
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool used;
+};
+constexpr int TMAP_SLOTS = 1024;  // direct-mapped
+
 static int make_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const long long* dims,
                      const long long* strides_elems, const int* box, bool mn_major = false) {
+  static TmapSlot* cache = nullptr;  // per process; the map embeds the pointer, which is device specific by construction
+  if (!cache) cache = static_cast<TmapSlot*>(calloc(TMAP_SLOTS, sizeof(TmapSlot)));
+  TmapKey key;
+  memset(&key, 0, sizeof key);
+  key.base = base, key.dtype = dtype, key.rank = rank, key.mn = mn_major ? 1 : 0;
+  for (int i = 0; i < rank; ++i) key.dims[i] = dims[i], key.strides[i] = i ? strides_elems[i] : 1, key.box[i] = box[i];
+  size_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < sizeof key; ++i) h = (h ^ reinterpret_cast<const unsigned char*>(&key)[i]) * 1099511628211ull;
+  TmapSlot* slot = cache ? &cache[h % TMAP_SLOTS] : nullptr;
+  if (slot && slot->used && slot->key == key) {
+    *m = slot->map;
+    return 0;
+  }
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(SZN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const int es = dtype == SZN_BF16 ? 2 : 4;
@@ -697,6 +759,73 @@ static int make_tmap(CUtensorMap* m, int dtype, const void* base, int rank, cons
     snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d) rank %d dims %lld %lld box %d %d", (int)r, rank,
              dims[0], dims[1], box[0], box[1]);
     return set_error(SZN_ERR_CUDA, msg);
+  }
+  if (slot) {
+    slot->key = key;
+    slot->map = *m;
+    slot->used = true;
+  }
+  return 0;
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// im2col-mode map of an NHWC tensor [B][H][W][pitch] (pitch >= C elements per pixel) for a conv with symmetric padding `pad`
+// and an R x S filter: a load lands 128 consecutive output pixels x `kc` channels at a tap offset (tma_load_im2col_4d).
+// Corner convention (CUDA driver API / CUTLASS copy_traits_sm90_im2col): lower = -pad, upper = pad - (filter - 1).
+static int make_tmap_im2col(CUtensorMap* m, int dtype, const void* base, long long C, long long pitch, int W, int H, int B,
+                            int R, int S, int pad, int kc) {
+  static TmapSlot* cache = nullptr;
+  if (!cache) cache = static_cast<TmapSlot*>(calloc(TMAP_SLOTS, sizeof(TmapSlot)));
+  TmapKey key;
+  memset(&key, 0, sizeof key);
+  key.base = base, key.dtype = dtype, key.rank = 4, key.mn = 2;  // mn = 2 marks the im2col flavour
+  key.dims[0] = C, key.dims[1] = W, key.dims[2] = H, key.dims[3] = B, key.dims[4] = pitch;
+  key.box[0] = kc, key.box[1] = R, key.box[2] = S, key.box[3] = pad;
+  size_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < sizeof key; ++i) h = (h ^ reinterpret_cast<const unsigned char*>(&key)[i]) * 1099511628211ull;
+  TmapSlot* slot = cache ? &cache[h % TMAP_SLOTS] : nullptr;
+  if (slot && slot->used && slot->key == key) {
+    *m = slot->map;
+    return 0;
+  }
+  static EncodeIm2colFn enc = nullptr;
+  if (!enc) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return set_error(SZN_ERR_CUDA, "cuTensorMapEncodeIm2col entry point not available");
+    enc = reinterpret_cast<EncodeIm2colFn>(ptr);
+  }
+  const int es = dtype == SZN_BF16 ? 2 : 4;
+  cuuint64_t gd[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gs[3] = {(cuuint64_t)pitch * es, (cuuint64_t)W * pitch * es, (cuuint64_t)H * W * pitch * es};
+  int lower[2] = {-pad, -pad}, upper[2] = {pad - (S - 1), pad - (R - 1)};  // (W, H)
+  cuuint32_t el[4] = {1, 1, 1, 1};
+  if (gs[0] % 16 || reinterpret_cast<uintptr_t>(base) % 16) return set_error(SZN_ERR_ARG, "im2col TMA: base / pixel pitch not 16-byte aligned");
+  CUresult r = enc(m, dtype == SZN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                   const_cast<void*>(base), gd, gs, lower, upper, (cuuint32_t)kc, 128, el, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[200];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeIm2col failed (%d): C %lld pitch %lld W %d H %d B %d R %d S %d pad %d", (int)r, C,
+             pitch, W, H, B, R, S, pad);
+    return set_error(SZN_ERR_CUDA, msg);
+  }
+  {
+    // drivers up to CUDA 13.1 mis-encode im2col maps of tensors smaller than 128 KB (the workaround CUTLASS ships in
+    // copy_traits_sm90_im2col.hpp: clear bit 21 of the second descriptor word)
+    static int drv = -1;
+    if (drv < 0 && cudaDriverGetVersion(&drv) != cudaSuccess) drv = 0;
+    if (drv <= 13010 && (unsigned long long)B * H * W * pitch * es < 131072ull) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+  }
+  if (slot) {
+    slot->key = key;
+    slot->map = *m;
+    slot->used = true;
   }
   return 0;
 }
@@ -858,14 +987,28 @@ static int conv_gemm(int dtype, const void* x, long long ldx, const void* wt, co
   if (R == 1 && S == 1 && pad == 0) {  // 1x1: flatten every pixel of the batch into one row of pixels
     Wq = B * H * W, Hq = 1, Bq = 1, Ho = 1, Wo = Wq;
   }
-  pick_tile(Wo, Ho, 128, &p.TW, &p.TH);
-  p.tiles_x = ceil_div(Wo, p.TW), p.tiles_y = ceil_div(Ho, p.TH), p.B = Bq;
+  // k > 1: M tiles are runs of 128 consecutive output pixels fetched by im2col-mode TMA (no rectangular tiles, so no
+  // padded tile rows: rectangles over-covered the 710 / 355 / 178 / 89 / 45-pixel maps by 8-14 %).  1x1: the flattened
+  // pixel row below is already that.  SZN_NO_IM2COL=1 keeps the rectangular tiles (A/B switch).
+  static int no_im2col = -1;
+  if (no_im2col < 0) no_im2col = getenv("SZN_NO_IM2COL") ? 1 : 0;
+  const bool im2col = !(R == 1 && S == 1 && pad == 0) && !no_im2col;
+  p.im2col = im2col ? 1 : 0;
+  p.m_total = (long long)Bq * Ho * Wo;
+  if (im2col) {
+    p.TW = 128, p.TH = 1;
+    p.tiles_x = ceil_div(p.m_total, 128), p.tiles_y = 1, p.B = 1;
+  } else {
+    pick_tile(Wo, Ho, 128, &p.TW, &p.TH);
+    p.tiles_x = ceil_div(Wo, p.TW), p.tiles_y = ceil_div(Ho, p.TH), p.B = Bq;
+  }
+  const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.B;
   p.H = Ho, p.W = Wo, p.R = R, p.S = S, p.pad = pad, p.Ck = Cin, p.kchunks = ceil_div(Cin, KC);
   p.N = Cout;
   const int out_f32 = (dtype == SZN_F32 || out_fp32) ? 1 : 0;
   const int ngran = out_f32 ? 32 : 64;  // the epilogue moves 128-byte output rows
   p.block_n = pick_block_n(Cout, ngran, Cout >= 256 ? 256 : 128);
-  p.block_n = fill_sms(p.block_n, Cout, ngran, (long long)p.tiles_x * p.tiles_y * Bq);
+  p.block_n = fill_sms(p.block_n, Cout, ngran, m_tiles);
   p.n_tiles = ceil_div(Cout, p.block_n);
   p.ldo = ldo, p.bias = bias, p.scale = scale, p.scale_ld = scale_ld, p.relu = relu, p.out_fp32 = out_fp32;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(scale)) & 15) == 0 && scale_ld % 4 == 0;
@@ -876,18 +1019,28 @@ static int conv_gemm(int dtype, const void* x, long long ldx, const void* wt, co
   {
     // split: a pixel row is [hi | lo], i.e. twice the row pitch with the plane as one more (outermost) dimension
     const long long opitch = (split && !out_f32) ? 2 * ldo : ldo, xpitch = split ? 2 * ldx : ldx;
-    long long od[5] = {Cout, Wo, Ho, Bq, 2}, os[5] = {1, opitch, (long long)Wo * opitch, (long long)Ho * Wo * opitch, ldo};
-    int obx[5] = {out_f32 ? 32 : 64, p.TW, p.TH, 1, 1};
-    if (int e = make_tmap(&to, out_f32 ? SZN_F32 : SZN_BF16, y, (split && !out_f32) ? 5 : 4, od, os, obx)) return e;
-    long long d[5] = {Cin, Wq, Hq, Bq, 2}, s[5] = {1, xpitch, (long long)Wq * xpitch, (long long)Hq * Wq * xpitch, ldx};
-    int bx[5] = {KC, p.TW, p.TH, 1, 1};
-    if (int e = make_tmap(&ta, edt, x, split ? 5 : 4, d, s, bx)) return e;
+    if (im2col) {
+      // output: the flat [pixels][channels] matrix (+ the plane as a third dimension in the split format)
+      long long od[3] = {Cout, p.m_total, 2}, os[3] = {1, opitch, ldo};
+      int obx[3] = {out_f32 ? 32 : 64, 128, 1};
+      if (int e = make_tmap(&to, out_f32 ? SZN_F32 : SZN_BF16, y, (split && !out_f32) ? 3 : 2, od, os, obx)) return e;
+      // input: NHWC, a pixel row holds Cin channels (split: [hi | lo] = 2 Cin bf16)
+      p.a_lo_ch = (int)ldx;
+      if (int e = make_tmap_im2col(&ta, edt, x, split ? ldx + Cin : Cin, xpitch, Wq, Hq, Bq, R, S, pad, KC)) return e;
+    } else {
+      long long od[5] = {Cout, Wo, Ho, Bq, 2}, os[5] = {1, opitch, (long long)Wo * opitch, (long long)Ho * Wo * opitch, ldo};
+      int obx[5] = {out_f32 ? 32 : 64, p.TW, p.TH, 1, 1};
+      if (int e = make_tmap(&to, out_f32 ? SZN_F32 : SZN_BF16, y, (split && !out_f32) ? 5 : 4, od, os, obx)) return e;
+      long long d[5] = {Cin, Wq, Hq, Bq, 2}, s[5] = {1, xpitch, (long long)Wq * xpitch, (long long)Hq * Wq * xpitch, ldx};
+      int bx[5] = {KC, p.TW, p.TH, 1, 1};
+      if (int e = make_tmap(&ta, edt, x, split ? 5 : 4, d, s, bx)) return e;
+    }
     long long K = (long long)R * S * Cin;
     long long d2[3] = {K, Cout, 2}, s2[3] = {1, K, (long long)Cout * K};  // split: hi plane, then lo plane
     int bx2[3] = {KC, p.block_n, 1};
     if (int e = make_tmap(&tb, edt, wt, split ? 3 : 2, d2, s2, bx2)) return e;
   }
-  const long long tiles = (long long)p.tiles_x * p.tiles_y * Bq * p.n_tiles;
+  const long long tiles = m_tiles * p.n_tiles;
   {
     // Which operand should concurrently running CTAs share through L2?  By default the pixel tile (N tiles fastest).
     // When the weights are far larger than L2 while the activations fit (fc6's data gradient: 411 MB of weights, 38 MB
