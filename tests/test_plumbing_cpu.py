@@ -109,8 +109,11 @@ def test_experimental_fused_head_routes_through_the_score_map(stubbed):
     del stubbed.names[:]
     loss = utils.cosine_loss(f, lab, table=table)
     assert stubbed.names == ["szn_head_fused_fwd"]
-    labels = utils.infer_lbl_device(f, table)
-    assert stubbed.names[-1] == "szn_head_fused_fwd" and labels.shape == (2, H, W)
+    labels = utils.infer_lbl_device(f, table)            # the loss pass already wrote them: no second launch
+    assert stubbed.names == ["szn_head_fused_fwd"] and labels.shape == (2, H, W) and labels is head.labels_cache[3]
+    other = table.clone()
+    assert utils.infer_lbl_device(f, other).shape == (2, H, W)   # another table: its own label-only launch
+    assert stubbed.names == ["szn_head_fused_fwd"] * 2
     utils.mse_loss(f, lab, table=table)
     assert stubbed.names == ["szn_head_fused_fwd"] * 3
     del stubbed.names[:]

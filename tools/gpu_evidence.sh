@@ -23,7 +23,7 @@ timeout 120 python tools/bench_layers.py bf16 8 5 > $O/r02_layers_bf16.txt 2>&1
 timeout 120 python tools/bench_layers.py fp32 8 5 > $O/r02_layers_fp32grade.txt 2>&1
 timeout 300 python tools/library_layers.py tf32 8 5 > $O/r02_library_layers_tf32.txt 2>&1; echo "library layers exit=$?"
 timeout 300 python tools/library_layers.py bf16 8 5 > $O/r02_library_layers_bf16.txt 2>&1
-timeout 60 ./tools/probe_mma > $O/r02_probe_mma.txt 2>&1
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/probe_mma tools/probe_mma.cu > /dev/null 2>&1 && timeout 60 ./tools/probe_mma > $O/r02_probe_mma.txt 2>&1
 fi
 if [ "${PART:-all}" = "all" ] || [ "$PART" = "3" ]; then
 B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
