@@ -48,6 +48,10 @@ def planes(dt):
     return 2 if dt == _lib.F32X3 else 1
 
 
+import os as _os
+_NO_FUSED_DB = _os.environ.get("SZN_NO_FUSED_DB") == "1"  # A/B switch: bias gradients through szn_bias_grad passes instead of the dgrad / pool_bwd epilogues
+
+
 def round_up(a, b):
     return (a + b - 1) // b * b
 
@@ -349,7 +353,7 @@ class FCN32sFunction(torch.autograd.Function):
         fused_db = {}
 
         def db_buffer(layer):
-            if not need[layer + ".bias"]:
+            if not need[layer + ".bias"] or _NO_FUSED_DB:
                 return None
             fused_db[layer] = zeros((P[layer + ".bias"].shape[0],))
             return fused_db[layer]
