@@ -1,0 +1,236 @@
+// conv1_1 (models.py:43-44,116: Conv2d(3, 64, 3, padding=100) + ReLU) on the tensor cores.
+//
+// The layer is HBM-bound on writing its 64-channel output (129 MB per 512 x 512 image in fp32), but as a CUDA-core
+// kernel it was bound by the shared-memory pipe (one LDS.128 per 4 FMAs: 0.33 of HBM).  Here it is the GEMM
+//   D[pixel, co] = sum_{k < 27} A[pixel, k] * W[co, k],   k = (r * 3 + s) * 3 + ci,   K padded to 32,
+// with the im2col rows BUILT IN SHARED MEMORY by four "builder" warps straight from the NCHW fp32 image (out-of-image
+// taps are zeros: that is the pad = 100), in the K-major SWIZZLE_128B layout tcgen05 reads.  The products are
+// error-compensated (3 x TF32: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, ~2^-21 per product), because the layer feeds every
+// precision mode -- the CUDA-core kernel it replaces was exact fp32 and the TF32 mode has no error budget to give away.
+//
+// Persistent, warp-specialised: warp 0 = MMA issuer, warps 1-4 = builders, warps 5-8 = epilogue (TMEM -> bias + ReLU ->
+// storage format -> swizzled staging -> coalesced 16-byte stores; a tile's 128 pixels are contiguous in NHWC).
+// Two A stages and two 64-column TMEM accumulators, so building tile i+1, the MMAs of tile i and the write-back of
+// tile i-1 overlap.  12 MMAs of 128 x 64 x 8 per tile (~1k cycles) against ~1.4k cycles of HBM time for its 32 KB.
+#include "szn_internal.h"
+#include "szn_ptx.cuh"
+#include "szn_store.cuh"
+
+namespace szn {
+
+constexpr int C11T_THREADS = 288;            // 9 warps
+constexpr int C11T_A_BYTES = 128 * 128;      // one plane of A: 128 rows x 32 fp32
+constexpr int C11T_B_BYTES = 64 * 128;       // one plane of W: 64 rows x 32 fp32
+
+template <typename T>
+__global__ void __launch_bounds__(C11T_THREADS, 1)
+conv1_1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /*OIHW [64][3][3][3]*/,
+                  const float* __restrict__ bias, void* __restrict__ y, int B, int H, int W, int Ho, int Wo, int pad,
+                  int num_tiles) {
+  using S = Store<T>;
+  constexpr int VN = S::VN;
+  constexpr bool SPLIT = sizeof(typename S::Raw) == 32;
+  constexpr int ROWB = (int)S::row_bytes(64);  // bytes of one output pixel row
+  constexpr int NCH = ROWB / 16;               // 16-byte chunks per output row: 16 (fp32, split) / 8 (bf16)
+  constexpr int NV = 64 / VN;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* a_st = smem;                                   // [2 stages][hi | lo][128 x 128 B]
+  uint8_t* b_st = a_st + 2 * 2 * C11T_A_BYTES;            // [hi | lo][64 x 128 B]
+  uint4* tile = reinterpret_cast<uint4*>(b_st + 2 * C11T_B_BYTES);  // [128][NCH] output staging
+  float* sb = reinterpret_cast<float*>(tile + 128 * 16);  // [64] bias
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sb + 64);  // [2] builders -> MMA (128 arrivals)
+  uint64_t* a_empty = a_full + 2;                           // [2] MMA -> builders (tcgen05.commit)
+  uint64_t* acc_full = a_empty + 2;                         // [2] MMA -> epilogue (tcgen05.commit)
+  uint64_t* acc_empty = acc_full + 2;                       // [2] epilogue -> MMA (4 warps)
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = warp_idx(), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 128);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tptr, 128);  // two accumulators of 64 fp32 columns
+    tmem_relinquish();
+  }
+  // W as the B operand: row co, k = (r*3+s)*3 + ci, hi / lo planes, K-major SWIZZLE_128B (16-byte chunk j of row r at j ^ (r & 7))
+  for (int i = threadIdx.x; i < 64 * 32; i += C11T_THREADS) {
+    const int co = i >> 5, k = i & 31;
+    float v = 0.f;
+    if (k < 27) {
+      const int tap = k / 3, ci = k - tap * 3;
+      v = w[co * 27 + ci * 9 + tap];
+    }
+    const float hi = to_tf32(v), lo = v - hi;
+    const int off = co * 128 + (((k >> 2) ^ (co & 7)) << 4) + ((k & 3) << 2);
+    *reinterpret_cast<float*>(b_st + off) = hi;
+    *reinterpret_cast<float*>(b_st + C11T_B_BYTES + off) = lo;
+  }
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+  const long long total = (long long)B * Ho * Wo;
+
+  if (warp == 0) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = umma_idesc(2, 0, 0, 128, 64);
+    const uint32_t b_hi = smem_u32(b_st), b_lo = b_hi + C11T_B_BYTES;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+      mbar_wait(&acc_empty[s], ph ^ 1u);  // the epilogue has drained this accumulator
+      mbar_wait(&a_full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_hi = smem_u32(a_st + s * 2 * C11T_A_BYTES), a_lo = a_hi + C11T_A_BYTES;
+        const uint32_t d = tmem + s * 64u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ah = umma_desc_sw128(a_hi + k * 32, 16, 1024), al = umma_desc_sw128(a_lo + k * 32, 16, 1024);
+          const uint64_t bh = umma_desc_sw128(b_hi + k * 32, 16, 1024), bl = umma_desc_sw128(b_lo + k * 32, 16, 1024);
+          tc_mma<true>(d, ah, bh, idesc, (uint32_t)(k != 0));
+          tc_mma<true>(d, al, bh, idesc, 1u);
+          tc_mma<true>(d, ah, bl, idesc, 1u);
+        }
+        tc_commit(&a_empty[s]);
+        tc_commit(&acc_full[s]);
+      }
+      __syncwarp();
+    }
+  } else if (warp <= 4) {
+    // =========================== builders: one im2col row per thread ===========================
+    const int r = threadIdx.x - 32;  // 0..127
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+      const long long pix = (long long)t * 128 + r;
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = 0.f;
+      if (pix < total) {
+        const int xo = (int)(pix % Wo);
+        const int yo = (int)((pix / Wo) % Ho);
+        const int b = (int)(pix / ((long long)Wo * Ho));
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+          for (int ss = 0; ss < 3; ++ss) {
+            const int yi = yo + rr - pad, xi = xo + ss - pad;
+            if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) v[(rr * 3 + ss) * 3 + c] = __ldg(x + (((long long)b * 3 + c) * H + yi) * W + xi);
+            }
+          }
+      }
+      mbar_wait(&a_empty[s], ph ^ 1u);  // the MMAs that read this stage two tiles ago have completed
+      uint4* hi_row = reinterpret_cast<uint4*>(a_st + s * 2 * C11T_A_BYTES + r * 128);
+      uint4* lo_row = reinterpret_cast<uint4*>(a_st + s * 2 * C11T_A_BYTES + C11T_A_BYTES + r * 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = to_tf32(v[4 * j + e]), l[e] = v[4 * j + e] - h[e];
+        hi_row[j ^ (r & 7)] = make_uint4(__float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]), __float_as_uint(h[3]));
+        lo_row[j ^ (r & 7)] = make_uint4(__float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]), __float_as_uint(l[3]));
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      mbar_arrive(&a_full[s]);
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int q4 = warp & 3;  // TMEM lane quarter this warp may read (warps 5..8 -> 1, 2, 3, 0)
+    const int row = q4 * 32 + lane;
+    const int et = threadIdx.x - 160;  // 0..127 among the epilogue threads
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+      mbar_wait(&acc_full[s], ph);
+      tc_fence_after();
+      float f[64];
+      {
+        uint32_t u[32];
+        const uint32_t tb = tmem + s * 64u + ((uint32_t)(q4 * 32) << 16);
+        tmem_ld32(tb, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(u[j]);
+        tmem_ld32(tb + 32u, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[32 + j] = __uint_as_float(u[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[s]);
+      // bias + ReLU -> storage format -> staging row `row`, chunk c at c ^ (row & (NCH-1)) (conflict-free)
+      uint4* trow = tile + row * NCH;
+      const int sw = row & (NCH - 1);
+#pragma unroll
+      for (int cv = 0; cv < NV; ++cv) {
+        float a[VN];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) a[e] = fmaxf(f[cv * VN + e] + sb[cv * VN + e], 0.f);
+        const typename S::Raw rr = S::from_float(a);
+        trow[cv ^ sw] = rr.a;
+        if constexpr (SPLIT) trow[(cv + NV) ^ sw] = rr.b;
+      }
+      named_bar_sync(2, 128);
+      const long long p0 = (long long)t * 128;
+      long long npix = total - p0;
+      if (npix > 128) npix = 128;
+      const int n16 = (int)(npix * NCH);
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + (size_t)p0 * ROWB);
+      for (int i = et; i < n16; i += 128) {
+        const int rw = i / NCH, c = i - rw * NCH;
+        __stcs(dst + i, tile[rw * NCH + (c ^ (rw & (NCH - 1)))]);
+      }
+      named_bar_sync(2, 128);  // the staging tile may be overwritten
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+template <typename T>
+static int launch_conv1_1_tc(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Ho, int Wo,
+                             int pad, cudaStream_t st) {
+  const long long total = (long long)B * Ho * Wo;
+  const int num_tiles = (int)((total + 127) / 128);
+  const size_t smem = 1024 + 2 * 2 * C11T_A_BYTES + 2 * C11T_B_BYTES + 128 * 16 * 16 + 64 * 4 + 8 * 8 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv1_1_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(SZN_ERR_CUDA, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  conv1_1_tc_kernel<T><<<grid, C11T_THREADS, smem, st>>>(x, w, bias, y, B, H, W, Ho, Wo, pad, num_tiles);
+  return check_launch("szn_conv1_1_fwd/tc");
+}
+
+// returns 0 on launch, < 0 on error
+int conv1_1_fwd_tc(int dtype, const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int pad,
+                   cudaStream_t st) {
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+  if (dtype == SZN_BF16) return launch_conv1_1_tc<__nv_bfloat16>(x, w, bias, y, B, H, W, Ho, Wo, pad, st);
+  if (dtype == SZN_F32X3) return launch_conv1_1_tc<SplitBf16>(x, w, bias, y, B, H, W, Ho, Wo, pad, st);
+  if (dtype == SZN_F32) return launch_conv1_1_tc<float>(x, w, bias, y, B, H, W, Ho, Wo, pad, st);
+  return set_error(SZN_ERR_ARG, "szn_conv1_1_fwd: bad dtype");
+}
+
+}  // namespace szn

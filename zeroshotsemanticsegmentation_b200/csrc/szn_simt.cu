@@ -2,6 +2,7 @@
 // conv1_1 (Cin=3, pad=100; models.py:43), 2x2 ceil-mode max-pool fwd/bwd (models.py:47..81),
 // bias gradients, weight layout packing, Dropout2d channel masks (models.py:86,91).
 #include "szn_internal.h"
+#include <stdlib.h>
 #include "szn_ptx.cuh"
 #include "szn_store.cuh"
 
@@ -576,8 +577,20 @@ extern "C" int szn_abi_version(void) { return 2; }
     }                                           \
   } while (0)
 
+namespace szn {
+int conv1_1_fwd_tc(int dtype, const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int pad,
+                   cudaStream_t st);  // szn_conv1_1_tc.cu
+}
+
 extern "C" int szn_conv1_1_fwd(int dtype, const float* x, const float* w_oihw, const float* bias, void* y, int B, int H,
                                int W, int pad, void* stream) {
+  // TF32 / bf16 storage: the tensor-core kernel (3 x TF32 GEMM over im2col rows built in shared memory: 0.50 -> 0.42 ms at
+  // B = 8, 512 x 512).  The fp32-grade mode keeps the CUDA-core kernel below, whose fp32 FMAs are exact to the last bit:
+  // with 3 x TF32 products (2^-21) in the FIRST layer, a few more ReLU gates flip downstream and the golden-size
+  // conv1_1.weight gradient moved from 6e-3 to 1.3e-2 rel-L2, past SURVEY 8d's 1e-2.  SZN_CONV1_1_SIMT=1 forces it everywhere.
+  static int simt = -1;
+  if (simt < 0) simt = getenv("SZN_CONV1_1_SIMT") ? 1 : 0;
+  if (!simt && dtype != SZN_F32X3) return conv1_1_fwd_tc(dtype, x, w_oihw, bias, y, B, H, W, pad, (cudaStream_t)stream);
   const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
   const long long total = (long long)B * Ho * Wo;
   const unsigned grid = (unsigned)((total + 127) / 128);

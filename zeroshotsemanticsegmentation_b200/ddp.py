@@ -40,7 +40,7 @@ class GradientAllReduce:
         if self.enabled:
             model._grad_ready = self._on_ready
             model._grad_flush = self._flush
-            if torch.cuda.is_available() and dist.get_backend(group) == "nccl":
+            if torch.cuda.is_available() and "nccl" in str(dist.get_backend(group)):
                 from . import _lib
                 # split-K work items per CTA of the weight gradient under data parallelism (include/szn.h)
                 _lib.call("szn_set_wgrad_waves", int(os.environ.get("SZN_DDP_WGRAD_WAVES", "1")))
