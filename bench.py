@@ -96,6 +96,12 @@ def hbm_bytes(name, a, es):
     if name == "szn_pool_bwd":          # reads y and dp, writes dy
         B, Hh, Ww, C = a[4:8]
         return B * Hh * Ww * C * es * 2.25
+    if name == "szn_pool_fwd_code":     # (dtype, in, out, code, B, H, W, C): + one routing byte per pooled element
+        B, Hh, Ww, C = a[4:8]
+        return B * Hh * Ww * C * (es * 1.25 + 0.25)
+    if name == "szn_pool_bwd_code":     # (dtype, code, dp, dy, B, H, W, C, ...): reads dp and the codes, writes dy
+        B, Hh, Ww, C = a[4:8]
+        return B * Hh * Ww * C * (es * 1.25 + 0.25)
     if name == "szn_upsample32_crop_fwd":   # (s, out, B, D, H, W, ...): writes the score
         B, D, Hh, Ww = a[2:6]
         return B * D * Hh * Ww * 4

@@ -78,6 +78,15 @@ int szn_pool_fwd(int dtype, const void* in, void* out, int B, int H, int W, int 
 int szn_pool_bwd(int dtype, const void* y, const void* dp, void* dy, int B, int H, int W, int C, int relu_gate,
                  float* dy_col_sum, void* stream);
 
+/* The same pair with a one-byte routing code per pooled element in place of the second read of the pre-pool tensor
+ * (the engine's default): code[B][Ho][Wo][C] = winner 0..3 (scan order, first maximum, as ATen's max_pool2d backward
+ * picks it) | 4 when that maximum is > 0 (the ReLU gate of the producer conv, models.py:46-47 etc.).  szn_pool_bwd_code
+ * gives exactly the dy of szn_pool_bwd from dp and the code alone, so the pre-pool activation is neither re-read nor kept.
+ * code must be 8-byte aligned. */
+int szn_pool_fwd_code(int dtype, const void* in, void* out, unsigned char* code, int B, int H, int W, int C, void* stream);
+int szn_pool_bwd_code(int dtype, const unsigned char* code, const void* dp, void* dy, int B, int H, int W, int C,
+                      int relu_gate, float* dy_col_sum, void* stream);
+
 /* db[C] += column sums of dy[rows][ld]  (stand-alone bias gradient; the conv layers get theirs fused into
  * szn_conv_dgrad / szn_pool_bwd, this entry point serves the 17x17 score heads; zero db first) */
 int szn_bias_grad(int dtype, const void* dy, float* db, long long rows, int C, long long ld, void* stream);

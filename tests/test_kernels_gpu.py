@@ -22,6 +22,10 @@ def lib():
 
 
 PRECS = ["tf32", "bf16", "fp32"]  # "fp32" = the split (hi, lo) bf16-plane format, 3 x bf16 products
+# kernels new in this build (csrc/szn_internal.h SZN_NEW_KERNELS_DEFAULT) are tested when they are the default or on request
+import os
+NEW_KERNELS = os.environ.get("SZN_TEST_NEW", "0") == "1"
+needs_new = pytest.mark.skipif(not NEW_KERNELS, reason="new-kernel variants: SZN_TEST_NEW=1")
 
 
 def round_to(t, prec):
@@ -254,7 +258,12 @@ def test_conv_wgrad(prec, case):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-def test_conv1_1(prec):
+@pytest.mark.parametrize("ctas", [pytest.param("2", marks=needs_new), "1"])
+def test_conv1_1(prec, ctas, monkeypatch):
+    # the tensor-core forward with two CTAs per SM (half-tile staging) and one (full-tile staging); the weight gradient in
+    # the re-blocked form (with "2") and the older one
+    monkeypatch.setenv("SZN_CONV1_1_TC_CTAS", ctas)
+    monkeypatch.setenv("SZN_CONV1_1_WGRAD_V2", "1" if ctas == "2" else "0")
     B, H, W = 2, 13, 21
     g = torch.Generator().manual_seed(5)
     x = torch.randn(B, 3, H, W, generator=g) * 50
@@ -274,6 +283,28 @@ def test_conv1_1(prec):
     gw = torch.zeros((64, 3, 3, 3), device=DEV)
     L.call("szn_conv1_1_wgrad", dcode(prec), dp(x.to(DEV)), dp(nhwc(dy, prec)), dp(gw), B, H, W, 100,
            st())
+    torch.cuda.synchronize()
+    assert relerr(gw.cpu(), dw) < 1e-4
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("v2", [pytest.param(True, marks=needs_new), False])
+@pytest.mark.parametrize("case", [(5, 130, 100), (9, 62, 100), (6, 63, 100), (8, 70, 1), (3, 200, 2)])
+def test_conv1_1_wgrad_row_segments(prec, case, v2, monkeypatch):
+    """Rows of the contributing window that span several 64-pixel segments (full, exactly full, 1- and 4-pixel tails) and
+    other paddings, through the re-blocked kernel and the older (co, ci, filter row) blocking (SZN_CONV1_1_WGRAD_V2, read
+    per call)."""
+    H, W, pad = case
+    B = 2
+    g = torch.Generator().manual_seed(50 + H)
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.zeros(64, 3, 3, 3, requires_grad=True)
+    pre = F.conv2d(x, w, padding=pad)
+    dy = round_to(torch.randn(pre.shape, generator=g), prec)
+    (dw,) = torch.autograd.grad(pre, w, dy)
+    monkeypatch.setenv("SZN_CONV1_1_WGRAD_V2", "1" if v2 else "0")
+    gw = torch.zeros((64, 3, 3, 3), device=DEV)
+    lib().call("szn_conv1_1_wgrad", dcode(prec), dp(x.to(DEV)), dp(nhwc(dy, prec)), dp(gw), B, H, W, pad, st())
     torch.cuda.synchronize()
     assert relerr(gw.cpu(), dw) < 1e-4
 
@@ -304,6 +335,37 @@ def test_pool(prec, hw):
     torch.cuda.synchronize()
     assert torch.equal(from_nhwc(dyo, prec), ref)
     assert relerr(csum.cpu(), ref.sum(dim=(0, 2, 3))) < 1e-5  # fused bias gradient of the conv in front of the pool
+    if not NEW_KERNELS:
+        return
+    # the routing-code pair: one byte per pooled element instead of re-reading y (bit-identical results)
+    out2 = act_buf(prec, B, p.shape[2], p.shape[3], C)
+    code = torch.full((B, p.shape[2], p.shape[3], C), 255, device=DEV, dtype=torch.uint8)
+    L.call("szn_pool_fwd_code", dcode(prec), dp(yd), dp(out2), dp(code), B, H, W, C, st())
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
+    yc = y.detach()
+    # reference codes: first maximum in scan order (ATen's choice) | 4 where it is positive
+    win = torch.zeros(p.shape, dtype=torch.int64)
+    best = torch.full(p.shape, float("-inf"))
+    for q in range(4):
+        sub = yc[:, :, (q >> 1)::2, (q & 1)::2]
+        pad_ = torch.full(p.shape, float("-inf"))
+        pad_[:, :, :sub.shape[2], :sub.shape[3]] = sub
+        take = pad_ > best
+        win[take], best[take] = q, pad_[take]
+    ref_code = (win + 4 * (best > 0)).permute(0, 2, 3, 1).to(torch.uint8)
+    assert torch.equal(code.cpu(), ref_code)
+    dyo2 = act_buf(prec, B, H, W, C)
+    csum2 = torch.zeros(C, device=DEV)
+    L.call("szn_pool_bwd_code", dcode(prec), dp(code), dp(nhwc(dpool, prec)), dp(dyo2), B, H, W, C, 1, dp(csum2), st())
+    torch.cuda.synchronize()
+    assert torch.equal(dyo2, dyo)
+    assert torch.equal(from_nhwc(dyo2, prec), ref)
+    assert relerr(csum2.cpu(), ref.sum(dim=(0, 2, 3))) < 1e-5
+    # without the ReLU gate the routed gradient is ATen's max_pool2d backward itself
+    L.call("szn_pool_bwd_code", dcode(prec), dp(code), dp(nhwc(dpool, prec)), dp(dyo2), B, H, W, C, 0, None, st())
+    torch.cuda.synchronize()
+    assert torch.equal(from_nhwc(dyo2, prec), dy)
 
 
 @pytest.mark.parametrize("prec", PRECS)

@@ -14,6 +14,7 @@ from zeroshotsemanticsegmentation_b200 import _lib, engine, models, utils
 class Recorder:
     def __init__(self):
         self.names = []
+        self.args = []
 
     def __call__(self, name, *args):
         sig = _lib.SIGNATURES[name]
@@ -26,6 +27,7 @@ class Recorder:
             else:
                 assert isinstance(a, int) and not isinstance(a, bool), "%s arg %d: int expected, got %r" % (name, i, type(a))
         self.names.append(name)
+        self.args.append(args)
 
 
 @pytest.fixture()
@@ -46,6 +48,7 @@ def run(model, x, mode="fcn"):
 
 
 D, C, H, W = 5, 7, 8, 12
+POOL_FWD, POOL_BWD = ("szn_pool_fwd", "szn_pool_bwd") if engine._POOL_Y else ("szn_pool_fwd_code", "szn_pool_bwd_code")
 
 
 def inputs(B=1):
@@ -54,20 +57,63 @@ def inputs(B=1):
             torch.randn(C, D, generator=g))
 
 
+def test_pool_routing_codes_replace_the_pre_pool_activations(stubbed, monkeypatch):
+    """Default: szn_pool_fwd_code writes a (B, Ho, Wo, C) uint8 code tensor per pool and the pre-pool activation is dropped
+    from the saved state; SZN_POOL_Y=1 (engine._POOL_Y) keeps the activation and the y-reading pair."""
+    monkeypatch.setattr(engine, "_POOL_Y", False)
+    m = models.FCN32s(D).train()
+    x, lab, table = inputs(1)
+    f, s = run(m, x)
+    sv = f.grad_fn.saved
+    assert sorted(sv["codes"]) == ["pool1", "pool2", "pool3", "pool4", "pool5"]
+    for pool, conv in (("pool1", "conv1_2"), ("pool2", "conv2_2"), ("pool3", "conv3_3"), ("pool4", "conv4_3"), ("pool5", "conv5_3")):
+        h, w, c = sv["dims"][pool]
+        assert sv["codes"][pool].shape == (1, h, w, c) and sv["codes"][pool].dtype == torch.uint8
+        assert sv["acts"][conv] is None and sv["acts"][pool] is not None
+    i = stubbed.names.index("szn_pool_fwd_code")
+    a = stubbed.args[i]
+    assert a[3] == sv["codes"]["pool1"].data_ptr() and tuple(a[4:8]) == (1,) + sv["dims"]["conv1_2"]
+    utils.cosine_loss(f, lab, table=table).backward()
+    i = stubbed.names.index("szn_pool_bwd_code")     # the first pool reached backwards is pool5
+    a = stubbed.args[i]
+    assert a[1] == sv["codes"]["pool5"].data_ptr() and tuple(a[4:8]) == (1,) + sv["dims"]["conv5_3"] and a[8] == 1
+    del stubbed.names[:], stubbed.args[:]
+    monkeypatch.setattr(utils, "_check_cuda", lambda *ts: None)
+    for frozen in (False, True):                     # inference / frozen trunk: no pool backward will run, plain pools
+        monkeypatch.setattr(m, "_grad_enabled", frozen, raising=False)
+        for n, p in m.named_parameters():
+            p.requires_grad_(not (frozen and n.startswith("conv")))
+        run(m, x)
+        assert stubbed.names.count("szn_pool_fwd") == 5 and "szn_pool_fwd_code" not in stubbed.names
+        del stubbed.names[:], stubbed.args[:]
+    for p in m.parameters():
+        p.requires_grad_(True)
+    monkeypatch.setattr(m, "_grad_enabled", True, raising=False)
+    run(m, x)
+    assert stubbed.names.count("szn_pool_fwd_code") == 5
+    monkeypatch.setattr(engine, "_POOL_Y", True)
+    del stubbed.names[:], stubbed.args[:]
+    f, s = run(m, x)
+    assert stubbed.names.count("szn_pool_fwd") == 5 and "szn_pool_fwd_code" not in stubbed.names
+    assert f.grad_fn.saved["codes"] == {} and f.grad_fn.saved["acts"]["conv1_2"] is not None
+    utils.cosine_loss(f, lab, table=table).backward()
+    assert stubbed.names.count("szn_pool_bwd") == 5 and "szn_pool_bwd_code" not in stubbed.names
+
+
 def test_default_path_calls_and_gradient_shapes(stubbed):
     m = models.FCN32s(D).train()
     x, lab, table = inputs(2)
     f, s = run(m, x)
     assert f.shape == (2, D, H, W) and s.shape == (2, 2, H, W) and f.is_contiguous()
     fwd = list(stubbed.names)
-    assert fwd[0] == "szn_conv1_1_fwd" and fwd.count("szn_conv_fwd") == 15 and fwd.count("szn_pool_fwd") == 5
+    assert fwd[0] == "szn_conv1_1_fwd" and fwd.count("szn_conv_fwd") == 15 and fwd.count(POOL_FWD) == 5
     assert fwd[-2:] == ["szn_upsample32_crop_fwd", "szn_deconv_small_fwd"] and "szn_dropout_scale" in fwd
     loss = utils.cosine_loss(f, lab, table=table)
     del stubbed.names[:]
     loss.backward()   # autograd validates every gradient's shape against its parameter
     bwd = stubbed.names
     assert bwd[0] == "szn_embed_loss_bwd" and "szn_upsample32_crop_bwd" in bwd
-    assert bwd.count("szn_conv_wgrad") == 15 and bwd.count("szn_conv_dgrad") == 15 and bwd.count("szn_pool_bwd") == 5
+    assert bwd.count("szn_conv_wgrad") == 15 and bwd.count("szn_conv_dgrad") == 15 and bwd.count(POOL_BWD) == 5
     assert bwd[-1] == "szn_conv1_1_wgrad"
     for n, p in m.named_parameters():
         if "upscore" in n or n.startswith("seenmask"):

@@ -21,6 +21,8 @@ O.forward(x, params, "fcn", collect=col_ref)
 def rel(a, b): return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 for name in list(sv["acts"].keys()) + ["fc6", "fc7"]:
     g = sv["acts"][name] if name in sv["acts"] else sv["h6" if name == "fc6" else "h7"]
+    if g is None:  # a pre-pool activation: dropped after the pool (routing codes), unless SZN_POOL_Y=1
+        continue
     g = g.float().cpu().permute(0, 3, 1, 2)
     print("%-8s vs emulated %.3e   vs fp32 %.3e   (emulated vs fp32 %.3e)" % (name, rel(g, col[name].detach()), rel(g, col_ref[name]), rel(col[name].detach(), col_ref[name])))
 print("score    vs emulated %.3e   vs fp32 %.3e" % (rel(f.detach().cpu(), f_em.detach()), rel(f.detach().cpu(), O.forward(x, params, "fcn"))))

@@ -26,6 +26,8 @@ SIGNATURES = {
     "szn_conv1_1_wgrad": [I, P, P, P, I, I, I, I, P],
     "szn_pool_fwd": [I, P, P, I, I, I, I, P],
     "szn_pool_bwd": [I, P, P, P, I, I, I, I, I, P, P],
+    "szn_pool_fwd_code": [I, P, P, P, I, I, I, I, P],
+    "szn_pool_bwd_code": [I, P, P, P, I, I, I, I, I, P, P],
     "szn_bias_grad": [I, P, P, LL, I, LL, P],
     "szn_pack_weight": [I, P, P, I, I, I, I, I, P],
     "szn_pack_weight_dgrad": [I, P, P, I, I, I, I, I, I, P],

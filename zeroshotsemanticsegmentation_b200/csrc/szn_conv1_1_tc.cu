@@ -12,6 +12,10 @@
 // storage format -> swizzled staging -> coalesced 16-byte stores; a tile's 128 pixels are contiguous in NHWC).
 // Two A stages and two 64-column TMEM accumulators, so building tile i+1, the MMAs of tile i and the write-back of
 // tile i-1 overlap.  12 MMAs of 128 x 64 x 8 per tile (~1k cycles) against ~1.4k cycles of HBM time for its 32 KB.
+// A CTA's builder and epilogue warps each run one latency chain per tile (gather -> split -> store; TMEM load -> convert ->
+// stage -> write out), so ONE CTA per SM leaves the SM waiting most of the time.  CTAS = 2 stages the output
+// in two 64-row halves (16 KB instead of 32 KB), which brings a CTA to 97 KB of shared memory and two of them onto an SM
+// (2 x 128 TMEM columns); CTAS = 1 is the full-tile staging form (SZN_CONV1_1_TC_CTAS = 1 | 2 selects, see szn_internal.h).
 #include "szn_internal.h"
 #include "szn_ptx.cuh"
 #include "szn_store.cuh"
@@ -22,8 +26,8 @@ constexpr int C11T_THREADS = 288;            // 9 warps
 constexpr int C11T_A_BYTES = 128 * 128;      // one plane of A: 128 rows x 32 fp32
 constexpr int C11T_B_BYTES = 64 * 128;       // one plane of W: 64 rows x 32 fp32
 
-template <typename T>
-__global__ void __launch_bounds__(C11T_THREADS, 1)
+template <typename T, int CTAS>
+__global__ void __launch_bounds__(C11T_THREADS, CTAS)
 conv1_1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /*OIHW [64][3][3][3]*/,
                   const float* __restrict__ bias, void* __restrict__ y, int B, int H, int W, int Ho, int Wo, int pad,
                   int num_tiles) {
@@ -33,6 +37,7 @@ conv1_1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /*OIH
   constexpr int ROWB = (int)S::row_bytes(64);  // bytes of one output pixel row
   constexpr int NCH = ROWB / 16;               // 16-byte chunks per output row: 16 (fp32, split) / 8 (bf16)
   constexpr int NV = 64 / VN;
+  constexpr int SROWS = 128 / CTAS;            // rows of the output staging buffer
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -40,7 +45,7 @@ conv1_1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /*OIH
   uint8_t* a_st = smem;                                   // [2 stages][hi | lo][128 x 128 B]
   uint8_t* b_st = a_st + 2 * 2 * C11T_A_BYTES;            // [hi | lo][64 x 128 B]
   uint4* tile = reinterpret_cast<uint4*>(b_st + 2 * C11T_B_BYTES);  // [128][NCH] output staging
-  float* sb = reinterpret_cast<float*>(tile + 128 * 16);  // [64] bias
+  float* sb = reinterpret_cast<float*>(tile + SROWS * 16);  // [64] bias
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sb + 64);  // [2] builders -> MMA (128 arrivals)
   uint64_t* a_empty = a_full + 2;                           // [2] MMA -> builders (tcgen05.commit)
   uint64_t* acc_full = a_empty + 2;                         // [2] MMA -> epilogue (tcgen05.commit)
@@ -173,29 +178,35 @@ conv1_1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /*OIH
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[s]);
-      // bias + ReLU -> storage format -> staging row `row`, chunk c at c ^ (row & (NCH-1)) (conflict-free)
-      uint4* trow = tile + row * NCH;
-      const int sw = row & (NCH - 1);
+      // bias + ReLU -> storage format -> staging row, chunk c at c ^ (row & (NCH-1)) (conflict-free); with CTAS = 2 the
+      // tile goes out in two halves of 64 rows (rows 0-63 belong to the warps with q4 = 0, 1)
+#pragma unroll 1
+      for (int half = 0; half < CTAS; ++half) {
+        if (row / SROWS == half) {
+          uint4* trow = tile + (row % SROWS) * NCH;
+          const int sw = row & (NCH - 1);
 #pragma unroll
-      for (int cv = 0; cv < NV; ++cv) {
-        float a[VN];
+          for (int cv = 0; cv < NV; ++cv) {
+            float a[VN];
 #pragma unroll
-        for (int e = 0; e < VN; ++e) a[e] = fmaxf(f[cv * VN + e] + sb[cv * VN + e], 0.f);
-        const typename S::Raw rr = S::from_float(a);
-        trow[cv ^ sw] = rr.a;
-        if constexpr (SPLIT) trow[(cv + NV) ^ sw] = rr.b;
+            for (int e = 0; e < VN; ++e) a[e] = fmaxf(f[cv * VN + e] + sb[cv * VN + e], 0.f);
+            const typename S::Raw rr = S::from_float(a);
+            trow[cv ^ sw] = rr.a;
+            if constexpr (SPLIT) trow[(cv + NV) ^ sw] = rr.b;
+          }
+        }
+        named_bar_sync(2, 128);
+        const long long p0 = (long long)t * 128 + half * SROWS;
+        long long npix = total - p0;
+        if (npix > SROWS) npix = SROWS;
+        const int n16 = npix > 0 ? (int)(npix * NCH) : 0;
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + (size_t)p0 * ROWB);
+        for (int i = et; i < n16; i += 128) {
+          const int rw = i / NCH, c = i - rw * NCH;
+          __stcs(dst + i, tile[rw * NCH + (c ^ (rw & (NCH - 1)))]);
+        }
+        named_bar_sync(2, 128);  // the staging buffer may be overwritten
       }
-      named_bar_sync(2, 128);
-      const long long p0 = (long long)t * 128;
-      long long npix = total - p0;
-      if (npix > 128) npix = 128;
-      const int n16 = (int)(npix * NCH);
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + (size_t)p0 * ROWB);
-      for (int i = et; i < n16; i += 128) {
-        const int rw = i / NCH, c = i - rw * NCH;
-        __stcs(dst + i, tile[rw * NCH + (c ^ (rw & (NCH - 1)))]);
-      }
-      named_bar_sync(2, 128);  // the staging tile may be overwritten
     }
   }
   tc_fence_before();
@@ -203,34 +214,43 @@ conv1_1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /*OIH
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-template <typename T>
+template <typename T, int CTAS>
 static int launch_conv1_1_tc(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Ho, int Wo,
                              int pad, cudaStream_t st) {
   const long long total = (long long)B * Ho * Wo;
   const int num_tiles = (int)((total + 127) / 128);
-  const size_t smem = 1024 + 2 * 2 * C11T_A_BYTES + 2 * C11T_B_BYTES + 128 * 16 * 16 + 64 * 4 + 8 * 8 + 16;
+  const size_t smem = 1024 + 2 * 2 * C11T_A_BYTES + 2 * C11T_B_BYTES + (128 / CTAS) * 16 * 16 + 64 * 4 + 8 * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv1_1_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv1_1_tc_kernel<T, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(SZN_ERR_CUDA, cudaGetErrorString(e));
     attr_set = true;
   }
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = num_tiles < sms ? num_tiles : sms;
-  conv1_1_tc_kernel<T><<<grid, C11T_THREADS, smem, st>>>(x, w, bias, y, B, H, W, Ho, Wo, pad, num_tiles);
+  const int grid = num_tiles < sms * CTAS ? num_tiles : sms * CTAS;
+  conv1_1_tc_kernel<T, CTAS><<<grid, C11T_THREADS, smem, st>>>(x, w, bias, y, B, H, W, Ho, Wo, pad, num_tiles);
   return check_launch("szn_conv1_1_fwd/tc");
+}
+
+template <int CTAS>
+static int dispatch_conv1_1_tc(int dtype, const float* x, const float* w, const float* bias, void* y, int B, int H, int W,
+                               int Ho, int Wo, int pad, cudaStream_t st) {
+  if (dtype == SZN_BF16) return launch_conv1_1_tc<__nv_bfloat16, CTAS>(x, w, bias, y, B, H, W, Ho, Wo, pad, st);
+  if (dtype == SZN_F32X3) return launch_conv1_1_tc<SplitBf16, CTAS>(x, w, bias, y, B, H, W, Ho, Wo, pad, st);
+  if (dtype == SZN_F32) return launch_conv1_1_tc<float, CTAS>(x, w, bias, y, B, H, W, Ho, Wo, pad, st);
+  return set_error(SZN_ERR_ARG, "szn_conv1_1_fwd: bad dtype");
 }
 
 // returns 0 on launch, < 0 on error
 int conv1_1_fwd_tc(int dtype, const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int pad,
                    cudaStream_t st) {
   const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
-  if (dtype == SZN_BF16) return launch_conv1_1_tc<__nv_bfloat16>(x, w, bias, y, B, H, W, Ho, Wo, pad, st);
-  if (dtype == SZN_F32X3) return launch_conv1_1_tc<SplitBf16>(x, w, bias, y, B, H, W, Ho, Wo, pad, st);
-  if (dtype == SZN_F32) return launch_conv1_1_tc<float>(x, w, bias, y, B, H, W, Ho, Wo, pad, st);
-  return set_error(SZN_ERR_ARG, "szn_conv1_1_fwd: bad dtype");
+  // read per call: A/B runs and tests switch it inside one process
+  if (env_flag("SZN_CONV1_1_TC_CTAS", SZN_NEW_KERNELS_DEFAULT ? 2 : 1) != 2)
+    return dispatch_conv1_1_tc<1>(dtype, x, w, bias, y, B, H, W, Ho, Wo, pad, st);
+  return dispatch_conv1_1_tc<2>(dtype, x, w, bias, y, B, H, W, Ho, Wo, pad, st);
 }
 
 }  // namespace szn

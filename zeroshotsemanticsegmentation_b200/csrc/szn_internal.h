@@ -4,10 +4,19 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/szn.h"
 
+// Default of the kernels that are new in this build (pool routing codes, re-blocked conv1_1 weight gradient, two conv1_1
+// tensor-core CTAs per SM).  Each has its own environment switch, read per call, so that one process can run both forms.
+#define SZN_NEW_KERNELS_DEFAULT 0
+
 namespace szn {
+inline int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && *e ? atoi(e) : dflt;
+}
 int set_error(int code, const char* msg);  // records msg for szn_last_error(), returns code
 void count_launch();                       // one more kernel of this library launched (szn_launch_count)
 

@@ -221,6 +221,122 @@ __global__ void __launch_bounds__(576) conv1_1_wgrad_kernel(const float* __restr
   atomicAdd(o + 2, acc2);
 }
 
+// Re-blocked form (the default): 192 threads = 64 output channels x 3 input channels, and a thread keeps all NINE taps
+// of its (co, ci) pair in registers.  A dY value is read from shared memory once per input channel instead of once per
+// (input channel, filter row) pair, and the three input rows come in as broadcast 16-byte loads of four pixels: 7 LDS per
+// 36 FMAs where the kernel above needs 24, which moves it from the shared-memory pipe to the FMA pipe.  Only
+// ceil(npx / 4) pixel quads of a segment are visited, so the 2-pixel tail segment of a 514-pixel row costs 1/16 of a
+// full one.
+constexpr int C11_NT = 192;
+constexpr int C11_XROW = C11_SEG + 4;  // staged input row: 64 + 2 halo columns, padded to whole float4s
+template <typename T>
+__global__ void __launch_bounds__(C11_NT) conv1_1_wgrad_v2_kernel(const float* __restrict__ x, const void* __restrict__ dy_,
+                                                                 float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
+                                                                 int pad, int ylo, int xlo, int wy, int nseg) {
+  constexpr bool SPLIT = sizeof(typename Store<T>::Raw) == 32;
+  typedef typename C11Stage<T>::type ST;
+  constexpr int VN = Store<T>::VN;
+  constexpr int NV = C11_SEG * 64 / VN;
+  constexpr int VPT = (NV + C11_NT - 1) / C11_NT;
+  constexpr int XE = 9 * C11_XROW, XPT = (XE + C11_NT - 1) / C11_NT;
+  __shared__ __align__(16) ST sdy[2][C11_SEG * 64];
+  __shared__ __align__(16) float xs[2][9][C11_XROW];  // [buffer][ci*3 + r][x]
+  const uint8_t* dy = reinterpret_cast<const uint8_t*>(dy_);
+  const int co = threadIdx.x & 63, ci = threadIdx.x >> 6;
+  float acc[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int t = 0; t < 3; ++t) acc[r][t] = 0.f;
+  const long long items = (long long)B * wy * nseg;
+  typename Store<T>::Raw rdy[VPT];
+  float rx[XPT];
+  auto seg_px = [&](long long it) {  // valid pixels of work item `it`
+    const int n = Wo - (xlo + (int)(it % nseg) * C11_SEG);
+    return n > C11_SEG ? C11_SEG : n;
+  };
+  auto fetch = [&](long long it) {
+    const int seg = (int)(it % nseg);
+    const int yo = ylo + (int)((it / nseg) % wy);
+    const int b = (int)(it / ((long long)nseg * wy));
+    const int xo0 = xlo + seg * C11_SEG;
+    const int npx = seg_px(it);
+    const long long row0 = ((long long)b * Ho + yo) * Wo + xo0;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int i = threadIdx.x + v * C11_NT;
+      const int px = i / (64 / VN), cv = i - px * (64 / VN);
+      rdy[v] = (i < NV && px < npx) ? Store<T>::template load_raw<true>(row_ptr<T>(dy, row0 + px, 64), 64, cv)
+                                    : Store<T>::zero();  // pixels past the row end count as 0
+    }
+#pragma unroll
+    for (int v = 0; v < XPT; ++v) {
+      const int i = threadIdx.x + v * C11_NT;
+      float val = 0.f;
+      if (i < XE) {
+        const int row = i / C11_XROW, col = i - row * C11_XROW;
+        const int c = row / 3, r = row - c * 3;
+        const int yi = yo + r - pad, xi = xo0 - pad + col;
+        if (yi >= 0 && yi < H && xi >= 0 && xi < W) val = __ldg(x + (((long long)b * 3 + c) * H + yi) * W + xi);
+      }
+      rx[v] = val;
+    }
+  };
+  int buf = 0;
+  if ((long long)blockIdx.x < items) fetch(blockIdx.x);
+  for (long long it = blockIdx.x; it < items; it += gridDim.x, buf ^= 1) {
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int i = threadIdx.x + v * C11_NT;
+      if (i < NV) {
+        if constexpr (SPLIT) {
+          float f[VN];
+          Store<T>::to_float(rdy[v], f);
+          float4* d4 = reinterpret_cast<float4*>(sdy[buf] + i * VN);
+          d4[0] = make_float4(f[0], f[1], f[2], f[3]);
+          d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+        } else {
+          reinterpret_cast<uint4*>(sdy[buf])[i] = rdy[v].a;
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < XPT; ++v) {
+      const int i = threadIdx.x + v * C11_NT;
+      if (i < XE) (&xs[buf][0][0])[i] = rx[v];
+    }
+    __syncthreads();  // double-buffered: the previous readers of this buffer passed the last barrier
+    if (it + gridDim.x < items) fetch(it + gridDim.x);
+    const int nq = (seg_px(it) + 3) >> 2;  // pixel quads with at least one valid pixel (the staged tail is zero)
+    const ST* d = sdy[buf] + co;
+    const float4* x0 = reinterpret_cast<const float4*>(xs[buf][ci * 3]);
+    const float4* x1 = reinterpret_cast<const float4*>(xs[buf][ci * 3 + 1]);
+    const float4* x2 = reinterpret_cast<const float4*>(xs[buf][ci * 3 + 2]);
+    float4 cur[3] = {x0[0], x1[0], x2[0]};
+#pragma unroll 2
+    for (int k = 0; k < nq; ++k) {
+      const float4 nxt[3] = {x0[k + 1], x1[k + 1], x2[k + 1]};
+      float dv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dv[j] = as_float<ST>(d[(4 * k + j) * 64]);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float wv[6] = {cur[r].x, cur[r].y, cur[r].z, cur[r].w, nxt[r].x, nxt[r].y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int t = 0; t < 3; ++t) acc[r][t] = fmaf(dv[j], wv[j + t], acc[r][t]);
+        cur[r] = nxt[r];
+      }
+    }
+  }
+  float* o = dw + co * 27 + ci * 9;  // OIHW
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int t = 0; t < 3; ++t) atomicAdd(o + r * 3 + t, acc[r][t]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // MaxPool2d(2, stride 2, ceil_mode=True) on NHWC, one channel vector (Store<T>::VN channels) per thread
 // ------------------------------------------------------------------------------------------------
@@ -322,6 +438,129 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const void* __restrict__ 
     for (int j = 0; j < VN; ++j) red[threadIdx.x * VN + j] = csum[j];
     __syncthreads();
     // threads t, t + cv, t + 2cv, ... hold the same channel vector (gridDim.x * 256 is a multiple of cv)
+    if ((int)threadIdx.x < cv) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        float t = 0.f;
+        for (int k = threadIdx.x; k < 256; k += cv) t += red[k * VN + j];
+        atomicAdd(col_sum + (((blockIdx.x * 256ll) + threadIdx.x) % cv) * VN + j, t);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same pool pair with a one-byte ROUTING CODE per pooled element instead of a second read of the pre-pool tensor:
+// code = winner (0..3, scan order, first maximum like ATen) | 4 if the maximum is > 0 (the producer's ReLU gate).
+// The forward pass writes it next to the pooled value (+1/16 of the pre-pool bytes in fp32 storage); the backward pass
+// reads dP and the code and writes dY: 1.31x the pre-pool tensor instead of 2.25x, and the pre-pool activation is not kept
+// for the backward pass at all.  Winner and gate are decided by the comparisons of pool_bwd_kernel, so dY is bit-identical.
+// ------------------------------------------------------------------------------------------------
+template <int VN>
+struct CodeVec;
+template <>
+struct CodeVec<4> {
+  typedef uint32_t type;
+};
+template <>
+struct CodeVec<8> {
+  typedef uint2 type;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pool_fwd_code_kernel(const void* __restrict__ in, void* __restrict__ out,
+                                                            uint8_t* __restrict__ code, int B, int H, int W, int C, int Ho,
+                                                            int Wo) {
+  using S = Store<T>;
+  constexpr int VN = S::VN;
+  const int cv = C / VN;
+  const long long total = (long long)B * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    long long r = i / cv;
+    const int xo = (int)(r % Wo);
+    r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float best[VN];
+    uint32_t win[VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) best[j] = -INFINITY, win[j] = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int y = 2 * yo + (q >> 1), x = 2 * xo + (q & 1);
+      if (y < H && x < W) {
+        float v[VN];
+        S::to_float(S::template load_raw<true>(row_ptr<T>(in, ((long long)b * H + y) * W + x, C), C, c), v);
+#pragma unroll
+        for (int j = 0; j < VN; ++j)
+          if (v[j] > best[j]) best[j] = v[j], win[j] = q;  // strict >: the first maximum in scan order wins
+      }
+    }
+    const long long orow = ((long long)b * Ho + yo) * Wo + xo;
+    S::template store_raw<false>(row_ptr<T>(out, orow, C), C, c, S::from_float(best));
+    uint32_t w[VN / 4];
+#pragma unroll
+    for (int k = 0; k < VN / 4; ++k) {
+      w[k] = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[k] |= (win[4 * k + j] | (best[4 * k + j] > 0.f ? 4u : 0u)) << (8 * j);
+    }
+    typename CodeVec<VN>::type* cp = reinterpret_cast<typename CodeVec<VN>::type*>(code + orow * C) + c;
+    if constexpr (VN == 4) *cp = w[0];
+    else *cp = make_uint2(w[0], w[1]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pool_bwd_code_kernel(const uint8_t* __restrict__ code, const void* __restrict__ dp,
+                                                            void* __restrict__ dy, int B, int H, int W, int C, int Ho, int Wo,
+                                                            int relu_gate, float* __restrict__ col_sum) {
+  using S = Store<T>;
+  constexpr int VN = S::VN;
+  const int cv = C / VN;
+  float csum[VN];  // see pool_bwd_kernel: a thread keeps one channel vector for the whole grid-stride loop
+#pragma unroll
+  for (int j = 0; j < VN; ++j) csum[j] = 0.f;
+  const long long total = (long long)B * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    long long r = i / cv;
+    const int xo = (int)(r % Wo);
+    r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    const long long orow = ((long long)b * Ho + yo) * Wo + xo;
+    float g[VN];
+    S::to_float(S::template load_raw<true>(row_ptr<T>(dp, orow, C), C, c), g);
+    uint32_t w[VN / 4];
+    const typename CodeVec<VN>::type* cp = reinterpret_cast<const typename CodeVec<VN>::type*>(code + orow * C) + c;
+    if constexpr (VN == 4) {
+      w[0] = __ldcs(cp);
+    } else {
+      const uint2 t = __ldcs(cp);
+      w[0] = t.x, w[1] = t.y;
+    }
+    float o[4][VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      const uint32_t cd = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+      const bool pass = !relu_gate || (cd & 4u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q][j] = (pass && (cd & 3u) == (uint32_t)q) ? g[j] : 0.f;
+      if (pass) csum[j] += g[j];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yy = 2 * yo + (q >> 1), xx = 2 * xo + (q & 1);
+      if (yy < H && xx < W) S::template store_raw<true>(row_ptr<T>(dy, ((long long)b * H + yy) * W + xx, C), C, c, S::from_float(o[q]));
+    }
+  }
+  if (col_sum) {
+    __shared__ float red[256 * VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) red[threadIdx.x * VN + j] = csum[j];
+    __syncthreads();
     if ((int)threadIdx.x < cv) {
 #pragma unroll
       for (int j = 0; j < VN; ++j) {
@@ -606,8 +845,23 @@ extern "C" int szn_conv1_1_wgrad(int dtype, const float* x, const void* dy, floa
   const int wy = yhi - ylo + 1, wx = xhi - xlo + 1;  // output pixels whose window touches the image
   const int nseg = (wx + C11_SEG - 1) / C11_SEG;
   const long long items = (long long)B * wy * nseg;
-  const int grid = (int)(items < 148 * 3 ? items : 148 * 3);
-  DISPATCH_T(dtype, (conv1_1_wgrad_kernel<T><<<grid, 576, 0, (cudaStream_t)stream>>>(x, dy, dw_oihw, B, H, W, Ho, Wo, pad, ylo, xlo, wy, nseg)));
+  if (!env_flag("SZN_CONV1_1_WGRAD_V2", SZN_NEW_KERNELS_DEFAULT)) {  // the (co, ci, filter row) blocking (switch read per call: A/B runs, tests)
+    const int grid = (int)(items < 148 * 3 ? items : 148 * 3);
+    DISPATCH_T(dtype, (conv1_1_wgrad_kernel<T><<<grid, 576, 0, (cudaStream_t)stream>>>(x, dy, dw_oihw, B, H, W, Ho, Wo, pad, ylo, xlo, wy, nseg)));
+    return check_launch("szn_conv1_1_wgrad");
+  }
+  static int per_sm[3] = {0, 0, 0}, sms = 0;  // resident CTAs per SM of each instantiation (persistent grid)
+  if (dtype < 0 || dtype > 2) return set_error(SZN_ERR_ARG, "bad dtype");
+  if (!per_sm[dtype]) {
+    int dev = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    DISPATCH_T(dtype, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv1_1_wgrad_v2_kernel<T>, C11_NT, 0)));
+    per_sm[dtype] = occ > 0 ? occ : 1;
+  }
+  const long long cap = (long long)sms * per_sm[dtype];
+  const int grid = (int)(items < cap ? items : cap);
+  DISPATCH_T(dtype, (conv1_1_wgrad_v2_kernel<T><<<grid, C11_NT, 0, (cudaStream_t)stream>>>(x, dy, dw_oihw, B, H, W, Ho, Wo, pad, ylo, xlo, wy, nseg)));
   return check_launch("szn_conv1_1_wgrad");
 }
 
@@ -638,6 +892,31 @@ extern "C" int szn_pool_bwd(int dtype, const void* y, const void* dp, void* dy, 
   }
   DISPATCH_T(dtype, (pool_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(y, dp, dy, B, H, W, C, Ho, Wo, relu_gate, dy_col_sum)));
   return check_launch("szn_pool_bwd");
+}
+
+extern "C" int szn_pool_fwd_code(int dtype, const void* in, void* out, unsigned char* code, int B, int H, int W, int C,
+                                 void* stream) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int vn = dtype == SZN_F32 ? 4 : 8;
+  if (C % vn) return set_error(SZN_ERR_ARG, "szn_pool_fwd_code: C must be a multiple of 16 bytes");
+  if (!code || (reinterpret_cast<uintptr_t>(code) & 7)) return set_error(SZN_ERR_ARG, "szn_pool_fwd_code: code must be an 8-byte aligned buffer");
+  const long long total = (long long)B * Ho * Wo * (C / vn);
+  DISPATCH_T(dtype, (pool_fwd_code_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, code, B, H, W, C, Ho, Wo)));
+  return check_launch("szn_pool_fwd_code");
+}
+
+extern "C" int szn_pool_bwd_code(int dtype, const unsigned char* code, const void* dp, void* dy, int B, int H, int W, int C,
+                                 int relu_gate, float* dy_col_sum, void* stream) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int vn = dtype == SZN_F32 ? 4 : 8;
+  if (C % vn) return set_error(SZN_ERR_ARG, "szn_pool_bwd_code: C must be a multiple of 16 bytes");
+  if (!code || (reinterpret_cast<uintptr_t>(code) & 7)) return set_error(SZN_ERR_ARG, "szn_pool_bwd_code: code must be an 8-byte aligned buffer");
+  const long long total = (long long)B * Ho * Wo * (C / vn);
+  if (dy_col_sum && 256 % (C / vn)) return set_error(SZN_ERR_UNSUPPORTED, "szn_pool_bwd_code: fused channel sums need C/vector to divide 256");
+  int grid = grid_for(total, 256);
+  if (dy_col_sum && grid > 148 * 4) grid = 148 * 4;  // every block ends with C atomics: fewer, longer-lived blocks (as szn_pool_bwd)
+  DISPATCH_T(dtype, (pool_bwd_code_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(code, dp, dy, B, H, W, C, Ho, Wo, relu_gate, dy_col_sum)));
+  return check_launch("szn_pool_bwd_code");
 }
 
 extern "C" int szn_bias_grad(int dtype, const void* dy, float* db, long long rows, int C, long long ld, void* stream) {

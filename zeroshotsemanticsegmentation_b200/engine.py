@@ -49,6 +49,10 @@ def planes(dt):
 
 
 import os as _os
+# SZN_POOL_CODE=1: one routing byte per pooled element (szn_pool_fwd_code / szn_pool_bwd_code) instead of keeping and
+# re-reading the pre-pool activation in the max-pool backward; 0: the y-reading pair.  New in this build.
+_NEW_KERNELS_DEFAULT = "0"
+_POOL_Y = _os.environ.get("SZN_POOL_CODE", _NEW_KERNELS_DEFAULT) != "1"
 _NO_FUSED_DB = _os.environ.get("SZN_NO_FUSED_DB") == "1"  # A/B switch: bias gradients through szn_bias_grad passes instead of the dgrad / pool_bwd epilogues
 
 
@@ -180,6 +184,10 @@ class FCN32sFunction(torch.autograd.Function):
 
         acts = {}   # name -> NHWC activation (post-ReLU / pooled)
         dims = {}   # name -> (H, W, C) of that activation
+        codes = {}  # pool name -> routing codes of szn_pool_fwd_code
+        # inference (no_grad) and head-only training (frozen trunk: trainer_seenmask.py) never run a pool backward
+        trunk_bwd = getattr(module, "_grad_enabled", True) and any(
+            g for n, g in zip(PARAM_ORDER, ctx.needs_input_grad[2:]) if n.startswith("conv"))
         # conv1_1 on CUDA cores straight from the NCHW image
         h, w_ = H + 198, W + 198
         a = torch.empty((B, h, w_, npl * 64), device=dev, dtype=tdtype)
@@ -187,12 +195,20 @@ class FCN32sFunction(torch.autograd.Function):
              ptr(P["conv1_1.bias"].detach()), ptr(a), B, H, W, 100, st)
         acts["conv1_1"], dims["conv1_1"] = a, (h, w_, 64)
         c = 64
+        prev_name = "conv1_1"
         for row in TRUNK[1:]:
             name = row[0]
             if len(row) == 1:
                 ho, wo = (h + 1) // 2, (w_ + 1) // 2
                 o = torch.empty((B, ho, wo, npl * c), device=dev, dtype=tdtype)
-                call("szn_pool_fwd", dt, ptr(a), ptr(o), B, h, w_, c, st)
+                if _POOL_Y or not trunk_bwd:
+                    call("szn_pool_fwd", dt, ptr(a), ptr(o), B, h, w_, c, st)
+                else:
+                    # winner + ReLU-gate byte per pooled element: all the backward pass needs of the pre-pool activation,
+                    # which is dropped here (conv1_2's output alone is 1 GB at B = 8, 512 x 512)
+                    codes[name] = torch.empty((B, ho, wo, c), device=dev, dtype=torch.uint8)
+                    call("szn_pool_fwd_code", dt, ptr(a), ptr(o), ptr(codes[name]), B, h, w_, c, st)
+                    acts[prev_name] = None
                 h, w_ = ho, wo
             else:
                 _, cin, cout, k, pad = row
@@ -203,6 +219,7 @@ class FCN32sFunction(torch.autograd.Function):
                 c = cout
             a = o
             acts[name], dims[name] = a, (h, w_, c)
+            prev_name = name
         # fc6 (7x7 valid) / fc7 (1x1) with ReLU and Dropout2d folded into the epilogue
         training = module.training
         drop = None
@@ -253,7 +270,7 @@ class FCN32sFunction(torch.autograd.Function):
              Dp, D, st)
 
         ctx.module = module
-        ctx.saved = dict(x=x, acts=acts, dims=dims, h6=h6, h7=h7, s17=s17, drop=drop, P=P, head_w=head_w,
+        ctx.saved = dict(x=x, acts=acts, dims=dims, codes=codes, h6=h6, h7=h7, s17=s17, drop=drop, P=P, head_w=head_w,
                          geom=(B, H, W, D, Dp, hs, ws), diag=diag, dt=dt, tdtype=tdtype)
         if getattr(module, "fused_head", False) and diag:
             # experimental: also hand out the hs x ws score map, so that the fused head (utils._FusedHeadLoss) can send its
@@ -423,8 +440,12 @@ class FCN32sFunction(torch.autograd.Function):
                 dy = torch.empty((B, ph, pw_, npl * pc), device=dev, dtype=tdtype)
                 vec = 8 if tdtype == torch.bfloat16 else 4
                 fuse = 256 % (pc // vec) == 0
-                call("szn_pool_bwd", dt, ptr(acts[prev]), ptr(g), ptr(dy), B, ph, pw_, pc, 1,
-                     ptr(db_buffer(prev)) if fuse else None, st)
+                if row[0] in sv["codes"]:
+                    call("szn_pool_bwd_code", dt, ptr(sv["codes"][row[0]]), ptr(g), ptr(dy), B, ph, pw_, pc, 1,
+                         ptr(db_buffer(prev)) if fuse else None, st)
+                else:
+                    call("szn_pool_bwd", dt, ptr(acts[prev]), ptr(g), ptr(dy), B, ph, pw_, pc, 1,
+                         ptr(db_buffer(prev)) if fuse else None, st)
                 g = dy
             else:
                 name, cin, cout, k, pad = row

@@ -130,6 +130,7 @@ class FCN32s(nn.Module):
             raise Exception("model given unexpected forward mode")
         if not x.is_cuda:
             raise RuntimeError("FCN32s (B200 build) runs on CUDA only: move the model and input to the GPU")
+        self._grad_enabled = torch.is_grad_enabled()  # the autograd function's forward always runs with grad mode off
         out = engine.FCN32sFunction.apply(self, x, *self._ordered_params())
         f, s = out[0], out[1]
         if len(out) == 3:  # fused_head: the score remembers the map it came from (see utils.ScoreHandle)
