@@ -572,8 +572,13 @@ def main():
             recs.append((name, a, e0, e1))
         return done
 
+    # one untimed step first: the legs before this one (API path, CPU arm, host copies) leave other kernels' data in L2 and
+    # the clocks wherever the power cap put them; a 2-step sample taken cold once showed the weight-gradient family 11 %
+    # slow while ms_per_step had not moved
+    resident()
+    torch.cuda.synchronize()
     _lib.set_profiler(prof)
-    prof_steps = 2
+    prof_steps = 4
     for _ in range(prof_steps):
         resident()
     torch.cuda.synchronize()

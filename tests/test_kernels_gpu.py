@@ -24,7 +24,7 @@ def lib():
 PRECS = ["tf32", "bf16", "fp32"]  # "fp32" = the split (hi, lo) bf16-plane format, 3 x bf16 products
 # kernels new in this build (csrc/szn_internal.h SZN_NEW_KERNELS_DEFAULT) are tested when they are the default or on request
 import os
-NEW_KERNELS = os.environ.get("SZN_TEST_NEW", "0") == "1"
+NEW_KERNELS = os.environ.get("SZN_TEST_NEW", "1") == "1"  # SZN_TEST_NEW=0 skips the variants that are not the default
 needs_new = pytest.mark.skipif(not NEW_KERNELS, reason="new-kernel variants: SZN_TEST_NEW=1")
 
 

@@ -3,7 +3,10 @@ cudnn.benchmark on, channels_last, TF32 allowed or bf16) -- forward, data gradie
 with CUDA events -- next to the same layer through libszn's tcgen05 kernel (tools/bench_layers.py prints those).
 The reference ships no GPU kernels of its own: this is what "the reference's conv on a B200" is.
 
-    python tools/library_layers.py [tf32|bf16] [B] [reps]
+    python tools/library_layers.py [tf32|bf16] [B] [reps] [layer,layer,...]
+
+(with a layer list under `ncu --metrics gpu__time_duration.sum` the launch list shows which cuDNN kernels won the
+cudnn.benchmark search: they are the ones repeated `reps` times at the end of each pass.)
 
 Not part of the product or of any parity claim; plain torch only (no oracle import).  Prints a table and one JSON line.
 """
@@ -34,6 +37,8 @@ for row in TRUNK:
     elif row[0] != "conv1_1":
         layers.append((row[0], h, w, row[1], row[2], row[3], row[4]))
 layers += [("fc6", h, w, 512, 4096, 7, 0), ("fc7", h - 6, w - 6, 4096, 4096, 1, 0)]
+if len(sys.argv) > 4:
+    layers = [l for l in layers if l[0] in sys.argv[4].split(",")]
 
 
 def timeit(fn):

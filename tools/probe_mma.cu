@@ -20,6 +20,25 @@ struct Cfg {
   int tf32, M, N, nacc, iters, issue;
 };
 
+// A operand read from TENSOR MEMORY (".ts" form: tcgen05.mma [d], [a_tmem], b_desc, ...): does an instruction still pay the
+// ~32 cycles a 128 x 32-byte A tile costs when it comes from shared memory?
+template <bool kTF32>
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kTF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
 __global__ void __launch_bounds__(128, 1) probe_kernel(Cfg c, long long* cycles_out) {
   extern __shared__ uint8_t raw[];
   const uint32_t a0 = smem_u32(raw);
@@ -68,7 +87,13 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Cfg c, long long* cycles_
         const int s = it & (STAGES - 1), k = (it >> 2) & 3, acc = it & (c.nacc - 1);
         const uint64_t ad = umma_desc_sw128(a_base + s * A_BYTES + k * 32, 16, 1024);
         const uint64_t bd = umma_desc_sw128(b_base + s * B_BYTES + k * 32, 16, 1024);
-        if (c.tf32) tc_mma<true>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
+        if (c.issue == 3) {
+          // A: M lanes x 8 columns (K = 8 tf32 or 16 packed bf16) of uninitialised tensor memory above the accumulators
+          // (columns 384..511, 16 slots taken in turn); values do not matter to the tensor pipe's timing
+          const uint32_t at = tmem + 384u + (uint32_t)((it & 15) * 8);
+          if (c.tf32) tc_mma_ts<true>(tmem + (uint32_t)(acc * acc_cols), at, bd, idesc, (uint32_t)(it >= c.nacc));
+          else tc_mma_ts<false>(tmem + (uint32_t)(acc * acc_cols), at, bd, idesc, (uint32_t)(it >= c.nacc));
+        } else if (c.tf32) tc_mma<true>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
         else tc_mma<false>(tmem + (uint32_t)(acc * acc_cols), ad, bd, idesc, (uint32_t)(it >= c.nacc));
       }
       tc_commit(bar);
@@ -175,6 +200,31 @@ int main() {
           printf("%-5s %4d %4d %5d | %10.1f | %10.0f | %.2fx%s\n", tf32 ? "tf32" : "bf16", c.M, c.N, c.nacc, cyc,
                  (double)c.M * c.N * kk / cyc, cyc / floor_c, issue ? "" : "   [threadIdx.x == 0 issue]");
         }
+  // ---- A from tensor memory ----
+  if (getenv("PROBE_TS")) {
+    printf("A operand in tensor memory (.ts), M = 128, elected-lane issue\n");
+    for (int tf32 = 1; tf32 >= 0; --tf32)
+      for (int ni = 0; ni < 5; ++ni) {
+        Cfg c{tf32, 128, Ns[ni], 1, 4096, 3};
+        for (int rep = 0; rep < 2; ++rep) {
+          probe_kernel<<<sms, 128, smem>>>(c, d);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) {
+            printf("ts launch failed (%s) for kind=%s N=%d\n", cudaGetErrorString(e), tf32 ? "tf32" : "bf16", c.N);
+            return 1;
+          }
+        }
+        cudaMemcpy(h, d, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+        long long worst = 0;
+        for (int i = 0; i < sms; ++i) worst = h[i] > worst ? h[i] : worst;
+        const double cyc = (double)worst / c.iters;
+        printf("%-5s %4d %4d %5d | %10.1f | %10.0f | A in TMEM\n", tf32 ? "tf32" : "bf16", c.M, c.N, c.nacc, cyc,
+               (double)c.M * c.N * (tf32 ? 8 : 16) / cyc);
+      }
+    cudaFree(d);
+    free(h);
+    return 0;
+  }
   // ---- CTA pairs ----
   if (cudaFuncSetAttribute(probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     printf("cudaFuncSetAttribute (pair) failed\n");

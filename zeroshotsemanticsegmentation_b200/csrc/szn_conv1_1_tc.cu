@@ -12,10 +12,10 @@
 // storage format -> swizzled staging -> coalesced 16-byte stores; a tile's 128 pixels are contiguous in NHWC).
 // Two A stages and two 64-column TMEM accumulators, so building tile i+1, the MMAs of tile i and the write-back of
 // tile i-1 overlap.  12 MMAs of 128 x 64 x 8 per tile (~1k cycles) against ~1.4k cycles of HBM time for its 32 KB.
-// A CTA's builder and epilogue warps each run one latency chain per tile (gather -> split -> store; TMEM load -> convert ->
-// stage -> write out), so ONE CTA per SM leaves the SM waiting most of the time.  CTAS = 2 stages the output
-// in two 64-row halves (16 KB instead of 32 KB), which brings a CTA to 97 KB of shared memory and two of them onto an SM
-// (2 x 128 TMEM columns); CTAS = 1 is the full-tile staging form (SZN_CONV1_1_TC_CTAS = 1 | 2 selects, see szn_internal.h).
+// CTAS = 2 (SZN_CONV1_1_TC_CTAS=2) stages the output in two 64-row halves (16 KB instead of 32 KB), which brings a CTA to
+// 97 KB of shared memory and two of them onto an SM (2 x 128 TMEM columns).  Measured on a B200 (B = 8, 512 x 512): 0.405 ms
+// with one CTA per SM and 0.405 ms with two -- the kernel is NOT bound by the latency chains of one CTA's builder and
+// epilogue warps (tensor pipe 11 %, l1tex 47 %, DRAM 30 % busy either way), so CTAS = 1 stays the default.
 #include "szn_internal.h"
 #include "szn_ptx.cuh"
 #include "szn_store.cuh"
@@ -248,7 +248,7 @@ int conv1_1_fwd_tc(int dtype, const float* x, const float* w, const float* bias,
                    cudaStream_t st) {
   const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
   // read per call: A/B runs and tests switch it inside one process
-  if (env_flag("SZN_CONV1_1_TC_CTAS", SZN_NEW_KERNELS_DEFAULT ? 2 : 1) != 2)
+  if (env_flag("SZN_CONV1_1_TC_CTAS", 1) != 2)
     return dispatch_conv1_1_tc<1>(dtype, x, w, bias, y, B, H, W, Ho, Wo, pad, st);
   return dispatch_conv1_1_tc<2>(dtype, x, w, bias, y, B, H, W, Ho, Wo, pad, st);
 }

@@ -8,9 +8,10 @@
 
 #include "../../include/szn.h"
 
-// Default of the kernels that are new in this build (pool routing codes, re-blocked conv1_1 weight gradient, two conv1_1
-// tensor-core CTAs per SM).  Each has its own environment switch, read per call, so that one process can run both forms.
-#define SZN_NEW_KERNELS_DEFAULT 0
+// Default of the kernels added last (re-blocked conv1_1 weight gradient: SZN_CONV1_1_WGRAD_V2; the Python side has the
+// same switch for the pool routing codes: engine.py SZN_POOL_CODE).  The switches are read per call, so one process can run
+// both forms (tests, A/B runs).
+#define SZN_NEW_KERNELS_DEFAULT 1
 
 namespace szn {
 inline int env_flag(const char* name, int dflt) {

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(576) conv1_1_wgrad_kernel(const float* __restr
   atomicAdd(o + 2, acc2);
 }
 
-// Re-blocked form (the default): 192 threads = 64 output channels x 3 input channels, and a thread keeps all NINE taps
+// Re-blocked form (the default, SZN_CONV1_1_WGRAD_V2): 192 threads = 64 output channels x 3 input channels, and a thread keeps all NINE taps
 // of its (co, ci) pair in registers.  A dY value is read from shared memory once per input channel instead of once per
 // (input channel, filter row) pair, and the three input rows come in as broadcast 16-byte loads of four pixels: 7 LDS per
 // 36 FMAs where the kernel above needs 24, which moves it from the shared-memory pipe to the FMA pipe.  Only
@@ -353,21 +353,25 @@ __global__ void pool_fwd_kernel(const void* __restrict__ in, void* __restrict__ 
     r /= Wo;
     const int yo = (int)(r % Ho);
     const int b = (int)(r / Ho);
+    // four independent loads in flight per thread; window positions outside the map (ceil mode) are clamped onto the last
+    // row / column, which repeats a value of the window and leaves the maximum unchanged
+    typename S::Raw raw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int y = 2 * yo + (q >> 1), x = 2 * xo + (q & 1);
+      y = y < H ? y : H - 1, x = x < W ? x : W - 1;
+      raw[q] = S::template load_raw<false>(row_ptr<T>(in, ((long long)b * H + y) * W + x, C), C, c);
+    }
     float m[VN];
 #pragma unroll
     for (int j = 0; j < VN; ++j) m[j] = -INFINITY;
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
+    for (int q = 0; q < 4; ++q) {
+      float v[VN];
+      S::to_float(raw[q], v);
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int y = 2 * yo + dy, x = 2 * xo + dx;
-        if (y < H && x < W) {
-          float v[VN];
-          S::to_float(S::template load_raw<false>(row_ptr<T>(in, ((long long)b * H + y) * W + x, C), C, c), v);
-#pragma unroll
-          for (int j = 0; j < VN; ++j) m[j] = fmaxf(m[j], v[j]);
-        }
-      }
+      for (int j = 0; j < VN; ++j) m[j] = fmaxf(m[j], v[j]);
+    }
     // tf32 / bf16: the maximum is one of the stored values, re-encoding it is exact.  split: hi + lo of the winner is
     // re-split, which reproduces the same fp32 value to 2^-17 (the planes themselves may differ in the last bit).
     S::template store_raw<false>(row_ptr<T>(out, ((long long)b * Ho + yo) * Wo + xo, C), C, c, S::from_float(m));
@@ -482,20 +486,27 @@ __global__ void __launch_bounds__(256) pool_fwd_code_kernel(const void* __restri
     r /= Wo;
     const int yo = (int)(r % Ho);
     const int b = (int)(r / Ho);
+    // All four loads are issued before the first comparison (four independent requests in flight per thread instead of a
+    // load -> compare chain behind four branches).  Window positions outside the map (ceil mode, odd H or W) are clamped
+    // onto the last row / column: that repeats a value seen EARLIER in scan order, which a strict > never lets win.
+    typename S::Raw raw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int y = 2 * yo + (q >> 1), x = 2 * xo + (q & 1);
+      y = y < H ? y : H - 1, x = x < W ? x : W - 1;
+      raw[q] = S::template load_raw<true>(row_ptr<T>(in, ((long long)b * H + y) * W + x, C), C, c);
+    }
     float best[VN];
     uint32_t win[VN];
 #pragma unroll
     for (int j = 0; j < VN; ++j) best[j] = -INFINITY, win[j] = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int y = 2 * yo + (q >> 1), x = 2 * xo + (q & 1);
-      if (y < H && x < W) {
-        float v[VN];
-        S::to_float(S::template load_raw<true>(row_ptr<T>(in, ((long long)b * H + y) * W + x, C), C, c), v);
+      float v[VN];
+      S::to_float(raw[q], v);
 #pragma unroll
-        for (int j = 0; j < VN; ++j)
-          if (v[j] > best[j]) best[j] = v[j], win[j] = q;  // strict >: the first maximum in scan order wins
-      }
+      for (int j = 0; j < VN; ++j)
+        if (v[j] > best[j]) best[j] = v[j], win[j] = q;  // strict >: the first maximum in scan order wins
     }
     const long long orow = ((long long)b * Ho + yo) * Wo + xo;
     S::template store_raw<false>(row_ptr<T>(out, orow, C), C, c, S::from_float(best));

@@ -64,6 +64,7 @@ struct UmmaParams {
   int relu, out_fp32;
   int vec_ok;  // bias / scale rows are 16-byte aligned
   float* col_sum;  // dgrad: += column sums of the stored output (the producer layer's bias gradient) or null
+  int cs_local;    // col_sum && one N tile: the CTA sums its tiles' columns in shared memory and adds them to col_sum once
   unsigned int* sched;  // {next tile, CTAs done}: global work counter of this launch (self-resetting, see launch())
   int im2col;           // MODE 0: M tiles are runs of 128 consecutive output pixels, A fetched by im2col-mode TMA
   long long m_total;    // MODE 0 im2col: output pixels B * Ho * Wo
@@ -192,6 +193,10 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* sqe = sqf + SQ;    // [SQ] tile index read by the MMA warp and the four epilogue warps
   int* sq_tile = reinterpret_cast<int*>(sqe + SQ);  // [SQ] tile index, -1 = no more work
   uint32_t* tptr = reinterpret_cast<uint32_t*>(sq_tile + SQ);
+  // [256] per-CTA column sums of the stored tiles (p.cs_local): conv1_2's data gradient has 31.5k tiles at B = 8, and one
+  // RED per (warp, column, tile) meant 8 M atomics onto the two cache lines that hold 64 bias gradients
+  float* cs_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 384);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) cs_smem[i] = 0.f;
 
   const int warp = warp_idx(), lane = threadIdx.x & 31;  // provably warp-uniform (see elect_one)
 
@@ -659,9 +664,19 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             const int col = nb + half * 32 + lane;
-            if (half * 32 < CW && col < p.N) atomicAdd(p.col_sum + col, v[0]);
+            if (half * 32 < CW && col < p.N) {
+              if (p.cs_local) atomicAdd(cs_smem + col, v[0]);  // one N tile: col < block_n <= 256
+              else atomicAdd(p.col_sum + col, v[0]);
+            }
           }
         }
+      }
+    }
+    if (MODE != 2 && p.cs_local) {
+      named_bar_sync(2, 128);  // every epilogue warp has added its last tile (barrier 1 belongs to emit())
+      for (int j = (int)threadIdx.x - 64; j < p.N; j += 128) {
+        const float v = cs_smem[j];
+        if (v != 0.f) atomicAdd(p.col_sum + j, v);
       }
     }
     if (issuer) bulk_wait<0>();  // all stores have landed before the CTA (and its shared memory) goes away
@@ -888,7 +903,8 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
                   cudaStream_t st) {
   if (MODE != 2 || p.mpair < 1 || SPLIT) p.mpair = 1;
   const int stage_bytes = (SPLIT ? 2 : 1) * (128 * 128 * p.mpair + p.block_n * 128);
-  const int fixed = 2 * 128 * 128 /* epilogue staging */ + 1024 /* alignment */ + 384 /* barriers, tile queue */;
+  const int fixed = 2 * 128 * 128 /* epilogue staging */ + 1024 /* alignment */ + 384 /* barriers, tile queue */ +
+                    1024 /* per-CTA column sums */;
   int stages = (227 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return set_error(SZN_ERR_UNSUPPORTED, "conv: tile does not leave two pipeline stages");
@@ -1015,6 +1031,7 @@ static int conv_gemm(int dtype, const void* x, long long ldx, const void* wt, co
   p.mask_ref = mask_ref;
   p.ld_mask = split ? 2 * ldo : ldo;
   p.col_sum = col_sum;
+  p.cs_local = (col_sum && p.n_tiles == 1 && p.block_n <= 256 && !env_flag("SZN_COLSUM_GLOBAL", 0)) ? 1 : 0;
   CUtensorMap ta, tb, to;
   {
     // split: a pixel row is [hi | lo], i.e. twice the row pitch with the plane as one more (outermost) dimension

@@ -51,7 +51,7 @@ def planes(dt):
 import os as _os
 # SZN_POOL_CODE=1: one routing byte per pooled element (szn_pool_fwd_code / szn_pool_bwd_code) instead of keeping and
 # re-reading the pre-pool activation in the max-pool backward; 0: the y-reading pair.  New in this build.
-_NEW_KERNELS_DEFAULT = "0"
+_NEW_KERNELS_DEFAULT = "1"
 _POOL_Y = _os.environ.get("SZN_POOL_CODE", _NEW_KERNELS_DEFAULT) != "1"
 _NO_FUSED_DB = _os.environ.get("SZN_NO_FUSED_DB") == "1"  # A/B switch: bias gradients through szn_bias_grad passes instead of the dgrad / pool_bwd epilogues
 
