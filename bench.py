@@ -740,10 +740,14 @@ def main():
         torch.cuda.empty_cache()
         cstep, cores, kind = cpu_step_fn(cfg, params, x_h[:1].clone(), lab_h[:1].clone(), table_h)
         t0 = time.perf_counter()
-        r = cstep()
-        dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": H * W / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": kind,
-                               "sample": cpu_sample_text(cfg, "; one cold pass, %.1f s, same weights and image as the GPU model" % dt)}
+        r = cstep()                      # the first (cold) pass also provides the parity numbers below
+        dt, passes = time.perf_counter() - t0, 1
+        while dt < 10.0 and passes < 8:  # a bounded sample of about 10 s of CPU work
+            cstep()
+            dt, passes = time.perf_counter() - t0, passes + 1
+        out["cpu_baseline"] = {"value": passes * H * W / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                               "sample": cpu_sample_text(cfg, "; %d passes over the same image (the first one cold), %.1f s in "
+                                                              "total, same weights and image as the GPU model" % (passes, dt))}
         import numpy as np
         out["parity"] = {
             "vs": "the CPU arm above (fp32), image 0 of the batch at full size, eval mode",
