@@ -184,6 +184,16 @@ def so_hash():
         return None
 
 
+def build_id():
+    """Hash of the kernel sources + flags libszn.so was built from (include/szn_build.h).  Unlike the hash of the .so it is
+    the same for every rebuild of the same sources (nvcc objects are not byte-reproducible)."""
+    try:
+        from zeroshotsemanticsegmentation_b200 import _lib
+        return _lib.build_id()
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
 def reference_modules():
     """(models, utils) of an UNMODIFIED reference checkout under baseline/_ref, or None.  /root/reference is never read
@@ -651,17 +661,21 @@ def main():
         peak, peak_note = bf16_peak, peak_src
     achieved = umma_flops / umma_ms / 1e9 if umma_ms else 0.0
     # DRAM bytes per launch of the same kernel family from the committed ncu capture of this command; only trusted when it
-    # was taken from THIS libszn.so (hash stamp) and this configuration
-    traffic, traffic_src = None, "no ncu capture for this build/config (profiles/r02_umma_traffic.json carries the .so hash it was taken from)"
+    # was taken from a libszn.so built from THESE kernel sources (build id = source hash, or the same .so file) and this
+    # configuration
+    traffic, traffic_src = None, "no ncu capture for this build/config (profiles/r02_umma_traffic.json carries the build id it was taken from)"
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_umma_traffic.json")))
         if tj.get("config") == args.config and tj.get("precision") == prec and not args.batch:
             if tj.get("so_sha256_16") == so_hash():
                 traffic, traffic_src = tj["umma_family_dram_bytes_per_launch"], "profiles/r02_umma_traffic.json (ncu dram__bytes, same libszn.so)"
+            elif tj.get("build_id") and tj.get("build_id") == build_id():
+                traffic, traffic_src = (tj["umma_family_dram_bytes_per_launch"],
+                                        "profiles/r02_umma_traffic.json (ncu dram__bytes, libszn.so built from the same kernel sources: build id %s)" % build_id())
             else:
                 traffic, traffic_src = (tj["umma_family_dram_bytes_per_launch"],
-                                        "profiles/r02_umma_traffic.json, taken from ANOTHER build of libszn.so (%s, this run %s): "
-                                        "indicative only" % (tj.get("so_sha256_16"), so_hash()))
+                                        "profiles/r02_umma_traffic.json, taken from ANOTHER build of libszn.so (build id %s, this run %s): "
+                                        "indicative only" % (tj.get("build_id") or tj.get("so_sha256_16"), build_id() or so_hash()))
     except Exception:
         pass
 
@@ -691,7 +705,7 @@ def main():
                      "frac_of_half_bf16_sustained": achieved / (bf16_peak / 2) if prec == "tf32" else None,
                      "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src},
         "kernels": kernels,
-        "libszn_sha256_16": so_hash(),
+        "libszn_sha256_16": so_hash(), "libszn_build_id": build_id(),
     }
     if tf32_measured:
         out["tf32_tflops_measured"] = tf32_measured

@@ -29,6 +29,21 @@ def test_library_exports_every_declared_symbol():
                                    "szn_comm_available"} == set(names)
 
 
+def test_library_is_built_from_the_sources_in_the_tree():
+    """include/szn_build.h: the library reports the hash of the sources it was compiled from; the Makefile computes the same
+    hash from the files in the tree.  nvcc objects are not byte-reproducible, so this -- not a hash of the .so -- is what
+    ties a profile (profiles/r02_umma_traffic.json: build_id) to a build."""
+    import subprocess
+    import __graft_entry__ as ge
+    ge.build()
+    from zeroshotsemanticsegmentation_b200 import _lib
+    want = subprocess.check_output(["make", "-s", "-C", os.path.join(ROOT, "zeroshotsemanticsegmentation_b200", "csrc"),
+                                    "print-hash"], text=True).strip()
+    assert len(want) == 16 and _lib.build_id() == want
+    hdr = open(os.path.join(ROOT, "include", "szn_build.h")).read()
+    assert "szn_build_id" in hdr
+
+
 def test_no_cpu_fallback():
     import zeroshotsemanticsegmentation_b200 as szn
     m = szn.FCN32s(4)

@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/gpu.txt 2>&1
 sha256sum zeroshotsemanticsegmentation_b200/libszn.so | cut -c1-16 > $O/r02_so_hash.txt
+python -c "from zeroshotsemanticsegmentation_b200 import _lib; print('build id (source hash, include/szn_build.h):', _lib.build_id())" >> $O/r02_so_hash.txt 2>&1
 if [ "${PART:-all}" = "all" ] || [ "$PART" = "1" ]; then
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -s > $O/r02_pytest_gpu.log 2>&1; echo "pytest exit=$? :: $(tail -1 $O/r02_pytest_gpu.log)"
 timeout 120 python __graft_entry__.py smoke > $O/r02_smoke.log 2>&1; echo "smoke exit=$? :: $(tail -1 $O/r02_smoke.log)"

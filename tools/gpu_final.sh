@@ -5,6 +5,7 @@ O=gpurun_out
 OLD="SZN_POOL_CODE=0 SZN_CONV1_1_WGRAD_V2=0 SZN_COLSUM_GLOBAL=1"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/gpu.txt 2>&1
 sha256sum zeroshotsemanticsegmentation_b200/libszn.so | cut -c1-16 > $O/r02_so_hash.txt
+python -c "from zeroshotsemanticsegmentation_b200 import _lib; print('build id (source hash, include/szn_build.h):', _lib.build_id())" >> $O/r02_so_hash.txt 2>&1
 # 1. the kernels touched last, both forms of each, fail-fast
 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -k "conv1_1 or pool or dgrad" --timeout 200 > $O/next_kernel_tests.log 2>&1; echo "kernel tests exit=$? :: $(tail -1 $O/next_kernel_tests.log)"
 SZN_COLSUM_GLOBAL=1 timeout 200 python -m pytest tests/test_kernels_gpu.py -q -k "dgrad" --timeout 200 > $O/next_kernel_tests_colsum_global.log 2>&1; echo "dgrad tests (global column sums) exit=$? :: $(tail -1 $O/next_kernel_tests_colsum_global.log)"

@@ -27,6 +27,19 @@ for (_, name), d in per.items():
     g[0] += 1
     g[1] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
     g[2] += d.get("gpu__time_duration.sum", 0.0)
+
+
+def build_id(path):
+    """include/szn_build.h: hash of the kernel sources the library was built from (None for a library older than that)."""
+    import ctypes
+    try:
+        lib = ctypes.CDLL(path)
+        lib.szn_build_id.restype = ctypes.c_char_p
+        return lib.szn_build_id().decode()
+    except Exception:
+        return None
+
+
 n = sum(g[0] for g in fam.values())
 tot = sum(g[1] for g in fam.values())
 so = os.path.join(ROOT, "zeroshotsemanticsegmentation_b200", "libszn.so")
@@ -34,6 +47,7 @@ print(json.dumps({
     "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:umma_conv_kernel "
               "-s 135 -c 45 python bench.py --steps 1 --warmup 3 (one step = 45 launches)",
     "config": config, "precision": prec, "so_sha256_16": hashlib.sha256(open(so, "rb").read()).hexdigest()[:16],
+    "build_id": build_id(so),
     "per_kernel": {k: {"launches": g[0], "dram_bytes": g[1], "ns": g[2], "dram_bytes_per_launch": g[1] / max(g[0], 1)}
                    for k, g in fam.items()},
     "umma_family_dram_bytes_per_launch": tot / max(n, 1), "umma_family_dram_bytes_per_step": tot, "launches": n}, indent=1))

@@ -81,8 +81,15 @@ def load():
     lib.szn_comm_available.restype = I
     lib.szn_head_fused_workspace_floats.argtypes = [I, I, I, I]
     lib.szn_head_fused_workspace_floats.restype = LL
+    lib.szn_build_id.argtypes = []
+    lib.szn_build_id.restype = ctypes.c_char_p
     _lib = lib
     return lib
+
+
+def build_id():
+    """Hash of the kernel sources and compiler flags this libszn.so was built from (include/szn_build.h)."""
+    return load().szn_build_id().decode()
 
 
 _profiler = None
