@@ -1,5 +1,6 @@
-"""Layer-by-layer comparison of the CUDA path with the storage-precision oracle (debug aid for the GPU box; lives under
-tests/ because only test infrastructure may import oracle/).  usage: python tests/diag_layers.py [tf32|bf16]"""
+"""Layer-by-layer comparison of the CUDA path with the storage-precision oracle.  NOT a test (pytest does not collect it:
+no test_ prefix): a debug aid for the GPU box that lives under tests/ because only test infrastructure may import oracle/.
+usage: python tests/diag_layers.py [tf32|bf16]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -39,7 +39,7 @@ for IDX in 0 4 35 36 43 44; do
   python tools/ncu_metrics.py $O/prof_r02_umma_$IDX.ncu-rep > $O/r02_ncu_full_umma_${IDX}_summary.txt 2>&1
   [ $IDX != 0 ] && [ $IDX != 44 ] && rm -f $O/prof_r02_umma_$IDX.ncu-rep
 done
-for K in conv1_1_tc_kernel conv1_1_wgrad_kernel pool_fwd_kernel pool_bwd_kernel upsample_fwd_kernel upsample_bwd_kernel embed_loss_fwd_kernel embed_loss_bwd_kernel embed_argmax_tc_kernel; do
+for K in conv1_1_tc_kernel conv1_1_wgrad_v2_kernel pool_fwd_code_kernel pool_bwd_code_kernel upsample_fwd_kernel upsample_bwd_kernel embed_loss_fwd_kernel embed_loss_bwd_kernel embed_argmax_tc_kernel; do
   timeout 300 ncu --set full --clock-control none -k regex:$K -s 3 -c 1 -f -o $O/prof_r02_$K $B --no-fused-head > $O/ncu_$K.log 2>&1
   python tools/ncu_metrics.py $O/prof_r02_$K.ncu-rep > $O/r02_ncu_full_${K}_summary.txt 2>&1; rm -f $O/prof_r02_$K.ncu-rep
 done
